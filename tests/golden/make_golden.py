@@ -1,0 +1,214 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) on the seeded
+scenarios of tests/scenarios.py with injected noise.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/<scenario>.npz.  The reference cannot travel to the GPU box, the fixtures do.
+Import shims (none touches arithmetic): a stub ``matplotlib`` package, the reference
+root on sys.path, and ``gpr_lib.Utils.Parameters_covariance_functions`` imported before any MPK model.
+Noise injection: ``_standard_normal`` of torch.distributions.{normal,multivariate_normal}, the
+policy's ``f_drop`` attribute and ``torch.randn`` (4PMS) are replaced by feeders that hand out the
+scenario's eps / masks in the reference's own draw order.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import scenarios  # noqa: E402
+
+REF = "/root/reference"
+
+
+def _import_reference():
+    shim = tempfile.mkdtemp()
+    os.makedirs(os.path.join(shim, "matplotlib"))
+    for f in ("__init__.py", "pyplot.py"):
+        open(os.path.join(shim, "matplotlib", f), "w").close()
+    sys.path.insert(0, shim)
+    sys.path.insert(0, REF)
+    import gpr_lib.Utils.Parameters_covariance_functions  # noqa: F401
+    import model_learning.Model_learning as ML
+    import policy_learning.Cost_function as CF
+    import policy_learning.MC_PILCO as MCP
+    import policy_learning.Policy as PO
+    return types.SimpleNamespace(ML=ML, CF=CF, MCP=MCP, PO=PO)
+
+
+T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+CPU = torch.device("cpu")
+
+
+def build_model(R, sc):
+    D = sc["D"]
+    dicts = []
+    for g in sc["gps"]:
+        rbf = dict(active_dims=np.arange(D), lengthscales_init=np.exp(g["log_ls"]), flg_train_lengthscales=True,
+                   lambda_init=np.array([g["lambda"]]), flg_train_lambda=False, sigma_n_init=np.array([g["sigma_n"]]),
+                   flg_train_sigma_n=True, mean_init=np.array([g["mean"]]), sigma_n_num=None, dtype=torch.float64, device=CPU)
+        if g["mpk"]:
+            mpk = dict(active_dims=np.arange(D), poly_deg=len(g["mpk"]), Sigma_pos_par_init_list=list(g["mpk"]),
+                       flg_train_Sigma_pos_par_list=[True] * len(g["mpk"]), dtype=torch.float64, device=CPU)
+            dicts.append([rbf, mpk])
+        else:
+            dicts.append(rbf)
+    m = sc["model"]
+    has_mpk = bool(sc["gps"][0]["mpk"])
+    if m["kind"] == "speed":
+        cls = R.ML.Speed_Model_learning_RBF_MPK_angle_state if has_mpk else R.ML.Speed_Model_learning_RBF_angle_state
+        ml = cls(num_gp=sc["E"], init_dict_list=dicts, T_sampling=m["T"], angle_indeces=m["angle"],
+                 not_angle_indeces=m["not_angle"], vel_indeces=m["vel"], not_vel_indeces=m["pos"])
+    else:
+        ml = R.ML.Model_learning_RBF(num_gp=sc["E"], init_dict_list=dicts)
+    ml.gp_inputs = T(sc["X"])
+    ml.gp_output_list = [T(sc["Y"][:, e:e + 1]) for e in range(sc["E"])]
+    ml.dim_state, ml.dim_input, ml.num_samples = sc["Ds"], sc["Du"], sc["N"]
+    with torch.no_grad():
+        for e in range(sc["E"]):
+            ml.pretrain_gp(e)
+    ml.set_eval_mode()
+    return ml
+
+
+def policy_kwargs(sc):
+    p = sc["policy"]
+    kw = dict(input_dim=sc["Du"], num_basis=p["nb"], lengthscales_init=p["lengthscales"], centers_init=p["centers"],
+              weight_init=p["weight"], flg_squash=p["u_max"] is not None, u_max=p["u_max"] if p["u_max"] is not None else 1,
+              flg_drop=True, flg_bias=p["bias"] is not None, bias_init=p["bias"])
+    if p["kind"] == "angles":
+        kw.update(state_dim=sc["Ds"], angle_indices=p["angle"], non_angle_indices=p["non_angle"])
+    elif p["kind"] == "target":
+        kw.update(state_dim=2 * sc["Ds"], target_traj=p["target_traj"])
+    else:
+        kw.update(state_dim=sc["Ds"], scale_factor=p["scale"])
+    return kw
+
+
+def build_policy(R, sc):
+    cls = {"angles": R.PO.Sum_of_gaussians_with_angles, "target": R.PO.Sum_of_gaussians_with_target_trajectory,
+           "plain": R.PO.Sum_of_gaussians}[sc["policy"]["kind"]]
+    pol = cls(**policy_kwargs(sc))
+    if sc["policy"]["bias"] is not None:
+        pol.f_linear.bias.data = T(sc["policy"]["bias"])
+    return pol
+
+
+def cost_spec(R, sc):
+    c = sc["cost"]
+    if c["kind"] == "cart_pole":
+        return R.CF.Cart_pole_cost, dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), angle_index=c["angle_index"], pos_index=c["pos_index"])
+    if c["kind"] == "sat_traj":
+        return R.CF.Expected_saturated_distance_from_trajectory, dict(target_traj=T(c["target_traj"]), lengthscales=T(c["ls"]))
+    if c["kind"] == "sat_target":
+        return R.CF.Expected_saturated_distance, dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), active_dims=c["active"])
+    raise KeyError(c["kind"])
+
+
+class Feeder:
+    """Hands out pre-drawn tensors in call order; checks the requested shape."""
+
+    def __init__(self, items):
+        self.items, self.i = list(items), 0
+
+    def __call__(self, shape, *a, **k):
+        x = self.items[self.i]; self.i += 1
+        assert tuple(shape) == tuple(x.shape), (tuple(shape), tuple(x.shape))
+        return x
+
+
+def run_scenario(R, name):
+    sc = scenarios.scenario(name)
+    out = {}
+    ml = build_model(R, sc)
+    rs = np.random.RandomState(7)
+    Xs = T(sc["X"][:5] + 0.1 * rs.randn(5, sc["D"]))
+    out["Xs"] = Xs.numpy()
+    for e, gp in enumerate(ml.gp_list):
+        out[f"Kss_{e}"] = gp.get_covariance(Xs, ml.gp_inputs).detach().numpy()
+        out[f"Knoise_{e}"] = gp.get_covariance(ml.gp_inputs, flg_noise=True).detach().numpy()
+        out[f"kdiag_{e}"] = gp.get_diag_covariance(Xs).detach().numpy()
+        out[f"alpha_{e}"] = ml.alpha_list[e].numpy()
+        out[f"Kinv_{e}"] = ml.K_X_inv_list[e].numpy()
+        mu, var = gp.get_estimate_from_alpha(ml.gp_inputs_tr_list[e], Xs, ml.alpha_list[e], ml.m_X_list[e], ml.K_X_inv_list[e])
+        out[f"pmean_{e}"], out[f"pvar_{e}"] = mu.detach().numpy(), var.detach().numpy()
+    if name == "c1":
+        thr = 0.5 * torch.sqrt(ml.gp_list[0].get_sigma_n_2())
+        with torch.no_grad():
+            out["sod_idx_0"] = np.array([int(i) for i in ml.gp_list[0].get_SOD(ml.gp_inputs, ml.gp_output_list[0], thr)])
+        out["sod_thr_0"] = thr.detach().numpy()
+
+    # ---- full rollout through the reference's apply_policy ----
+    cost_cls, cost_par = cost_spec(R, sc)
+    common = dict(T_sampling=sc["model"]["T"] or 0.05, state_dim=sc["Ds"], input_dim=sc["Du"], f_sim=None,
+                  f_model_learning=lambda: ml, model_learning_par={}, f_rand_exploration_policy=R.PO.Random_exploration,
+                  rand_exploration_policy_par=dict(state_dim=sc["Ds"], input_dim=sc["Du"]),
+                  f_control_policy=lambda: build_policy(R, sc), control_policy_par={}, f_cost_function=cost_cls,
+                  cost_function_par=cost_par)
+    if "pms" in sc:
+        obj = R.MCP.MC_PILCO4PMS(pos_indeces=sc["pms"]["pos_idx"], vel_indeces=sc["pms"]["vel_idx"],
+                                 filtering_dict={"fc": sc["pms"]["fc"]},
+                                 std_meas_noise=np.array([sc["pms"]["std_pos"][0], 0.0, sc["pms"]["std_pos"][1], 0.0]), **common)
+    else:
+        obj = R.MCP.MC_PILCO(**common)
+    pol = obj.control_policy
+    M, H, nb, p = sc["M"], sc["H"], sc["policy"]["nb"], sc["p_dropout"]
+
+    feed = Feeder([T(sc["eps0"])] + [T(sc["eps"][t]) for t in range(H - 1)])
+    import torch.distributions.multivariate_normal as mvn
+    import torch.distributions.normal as nrm
+    old = (nrm._standard_normal, mvn._standard_normal, torch.randn)
+    nrm._standard_normal = feed
+    mvn._standard_normal = feed
+    masks = [T(sc["masks"][t]).reshape(M, 1, nb) for t in range(H)]
+    cnt = [0]
+
+    def f_drop(x, pp):
+        mk = masks[cnt[0]]; cnt[0] += 1
+        return x * mk / (1.0 - pp)
+    pol.f_drop = f_drop
+    if "pms" in sc:
+        mfeed = Feeder([T(sc["meas_eps"][t]) for t in range(H - 1)])
+        torch.randn = lambda *shape, **k: mfeed(shape)
+    try:
+        states, inputs = obj.apply_policy(particles_initial_state_mean=T(sc["x0_mean"]), particles_initial_state_var=T(sc["x0_var"]),
+                                          flg_particles_init_uniform=False, particles_init_up_bound=None, particles_init_low_bound=None,
+                                          flg_particles_init_multi_gauss=False, num_particles=M, T_control=H, p_dropout=p)
+    finally:
+        nrm._standard_normal, mvn._standard_normal, torch.randn = old
+    cost, std_cost = obj.cost_function(states, inputs, 0)
+    cost.backward()
+    out.update(states=states.detach().numpy(), inputs=inputs.detach().numpy(), cost=cost.detach().numpy(),
+               std_cost=std_cost.detach().numpy(), g_log_ls=pol.log_lengthscales.grad.numpy(), g_centers=pol.centers.grad.numpy(),
+               g_W=pol.f_linear.weight.grad.numpy())
+    if pol.f_linear.bias is not None and pol.f_linear.bias.grad is not None:
+        out["g_bias"] = pol.f_linear.bias.grad.numpy()
+    # single-step model outputs at t=0 (mean/var of the GP deltas) for the step-level parity test
+    with torch.no_grad():
+        x0 = T(out["states"][0]); u0 = T(out["inputs"][0])
+        nrm._standard_normal = Feeder([T(sc["eps"][0])])
+        try:
+            nxt, mu, var = ml.get_next_state(x0, u0)
+        finally:
+            nrm._standard_normal = old[0]
+        out.update(step_next=nxt.numpy(), step_mu=mu.numpy(), step_var=var.numpy())
+    # remaining cost kinds on the same states (forward values only)
+    st = states.detach()
+    if name == "delta":
+        c = sc["cost"]
+        cd, _ = R.CF.Expected_distance(target_state=T(c["target"]), lengthscales=T(c["ls"]), active_dims=c["active"])(st, None)
+        out["cost_distance"] = cd.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "cost", float(cost), "std", float(std_cost), "|g_centers|", float(np.abs(out["g_centers"]).max()),
+          "min var", min(float(out[f"pvar_{e}"].min()) for e in range(sc["E"])))
+
+
+if __name__ == "__main__":
+    R = _import_reference()
+    torch.set_num_threads(1)
+    for nm in scenarios.ALL:
+        run_scenario(R, nm)
