@@ -1,0 +1,31 @@
+// Host launcher of the FP64 tensor-core NT GEMM (see mcp_dgemm.cuh).
+#include "mcp_dgemm.cuh"
+
+namespace mcp {
+
+template <int BM, int BN, int WM, int WN>
+static int launch(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C,
+                  int ldc, int tri, int kflags, cudaStream_t st) {
+  auto kern = dgemm_nt_kernel<BM, BN, WM, WN>;
+  static bool configured = false;
+  constexpr size_t smem = gemm_smem_bytes<BM, BN>();
+  if (!configured) {
+    MCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  kern<<<grid, 32 * WM * WN, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+int dgemm_nt(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C,
+             int ldc, int tri, int kflags, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return MCP_OK;
+  MCP_CHECK_ARG((lda % 2 == 0) && (ldb % 2 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0),
+                "dgemm_nt: operands must be 16-byte aligned with even leading dimensions (lda=%d ldb=%d)", lda, ldb);
+  if ((size_t)M * N >= (size_t)512 * 512 && N >= 128) return launch<128, 128, 4, 2>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
+  return launch<64, 64, 2, 2>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
+}
+
+}  // namespace mcp

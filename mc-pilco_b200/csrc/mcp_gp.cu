@@ -1,0 +1,370 @@
+// GP side of the hot path: covariance evaluation, the per-model-update precompute (blocked Cholesky,
+// triangular inverse, K^-1, alpha) and the posterior mean/variance with their input Jacobians.
+// Reference behaviour being reproduced: gpr_lib/GP_prior/GP_prior.py:91-155 and the kernel classes
+// cited in mcp_kfn.cuh; driven by model_learning/Model_learning.py:163-208,265-336.
+#include "mcp_dgemm.cuh"
+#include "mcp_kfn.cuh"
+
+namespace mcp {
+
+// ------------------------------------------------------------------------------------------------
+// covariance matrices
+// ------------------------------------------------------------------------------------------------
+// K[i][j] = k(X1_i, X2_j) for i < n1, j < n2; columns n2..ncols_out-1 are written as zero (row padding for
+// the 16-byte tile loads of the GEMM).  add_noise adds sigma_n2 on the diagonal (X2 == X1 case).
+template <int DT>
+__global__ void __launch_bounds__(256) cov_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X1, int n1,
+                                                  const double* __restrict__ X2, int n2, int add_noise, double* __restrict__ K,
+                                                  int ldk, int ncols_out) {
+  int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+  if (j >= ncols_out) return;
+  double y[DT];
+  if (j < n2) KFn<DT>::load(y, X2 + (size_t)j * s.D, s.D);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int i = i0 + r;
+    if (i >= n1) break;
+    double v = 0.0;
+    if (j < n2) {
+      double x[DT];
+      KFn<DT>::load(x, X1 + (size_t)i * s.D, s.D);
+      v = KFn<DT>::k(s, x, y);
+      if (add_noise && i == j) v += s.sigma_n2;
+    }
+    K[(size_t)i * ldk + j] = v;
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) kdiag_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X, int n,
+                                                    double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[DT];
+  KFn<DT>::load(x, X + (size_t)i * s.D, s.D);
+  out[i] = KFn<DT>::kdiag(s, x);
+}
+
+static int launch_cov(const McpGpSpec& s, const double* X1, int n1, const double* X2, int n2, int add_noise, double* K, int ldk,
+                      int ncols_out, cudaStream_t st) {
+  if (n1 <= 0 || ncols_out <= 0) return MCP_OK;
+  dim3 grid(cdiv(ncols_out, 32), cdiv(n1, 32));
+  MCP_DISPATCH_D(s.D, (cov_kernel<DT><<<grid, 256, 0, st>>>(s, X1, n1, X2, n2, add_noise, K, ldk, ncols_out)));
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+static int check_spec(const McpGpSpec* s) {
+  MCP_CHECK_ARG(s != nullptr, "null gp spec");
+  MCP_CHECK_ARG(s->D >= 1 && s->D <= MCP_MAX_D, "gp input dim %d outside [1,%d]", s->D, MCP_MAX_D);
+  MCP_CHECK_ARG(s->n_poly >= 0 && s->n_poly <= MCP_MAX_POLY, "n_poly %d outside [0,%d]", s->n_poly, MCP_MAX_POLY);
+  for (int p = 0; p < s->n_poly; p++)
+    MCP_CHECK_ARG(s->poly_deg[p] >= 1 && s->poly_deg[p] <= MCP_MAX_DEG, "poly_deg[%d]=%d outside [1,%d]", p, s->poly_deg[p], MCP_MAX_DEG);
+  MCP_CHECK_ARG(s->has_se || s->n_poly > 0, "empty kernel");
+  return MCP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// precompute: blocked right-looking Cholesky (NB = 64) + blocked triangular inverse
+// ------------------------------------------------------------------------------------------------
+constexpr int NB = 64;
+
+// Factor one 64x64 diagonal block in place (lower), and write inv(L_kk) (lower, dense 64x64) to `invL`.
+// Non-SPD input yields NaN (sqrt of a negative pivot) which propagates, like every numerical failure here.
+__global__ void __launch_bounds__(256) potrf_block_kernel(double* __restrict__ Akk, int lda, double* __restrict__ invL) {
+  __shared__ double s[NB][NB + 1];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 256) s[e / NB][e % NB] = Akk[(size_t)(e / NB) * lda + (e % NB)];
+  __syncthreads();
+  for (int j = 0; j < NB; j++) {
+    if (tid == 0) s[j][j] = sqrt(s[j][j]);
+    __syncthreads();
+    if (tid > j && tid < NB) s[tid][j] /= s[j][j];
+    __syncthreads();
+    // trailing update of the lower triangle: s[i][k] -= s[i][j] * s[k][j], j < k <= i
+    int rem = NB - 1 - j;
+    for (int e = tid; e < rem * rem; e += 256) {
+      int i = j + 1 + e / rem, k = j + 1 + e % rem;
+      if (k <= i) s[i][k] -= s[i][j] * s[k][j];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) {
+    int i = e / NB, k = e % NB;
+    Akk[(size_t)i * lda + k] = (k <= i) ? s[i][k] : 0.0;
+  }
+  // inverse by forward substitution, one column per thread (each thread re-reads only its own writes)
+  if (tid < NB) {
+    const int c = tid;
+    for (int i = 0; i < NB; i++) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; k++) acc -= s[i][k] * invL[k * NB + c];
+      invL[i * NB + c] = (i < c) ? 0.0 : acc / s[i][i];
+    }
+  }
+}
+
+// dst[i][j] = src[j][i] for a 64x64 block
+__global__ void transpose_block_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd) {
+  __shared__ double t[NB][NB + 1];
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) t[e / NB][e % NB] = src[(size_t)(e / NB) * lds + e % NB];
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(size_t)(e / NB) * ldd + e % NB] = t[e % NB][e / NB];
+}
+
+__global__ void pad_identity_kernel(double* K, int ld, int n, int np) {
+  int i = n + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) K[(size_t)i * ld + i] = 1.0;
+}
+
+// dst = lower triangle of src, zeros above
+__global__ void lower_copy_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int n) {
+  int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+  if (i < n && j < n) dst[(size_t)i * ldd + j] = (j <= i) ? src[(size_t)i * lds + j] : 0.0;
+}
+
+// copy the lower triangle of src (computed) into a full symmetric dst [n x n]
+__global__ void symmetrize_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int n) {
+  int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+  if (i < n && j < n) dst[(size_t)i * ldd + j] = (j <= i) ? src[(size_t)i * lds + j] : src[(size_t)j * lds + i];
+}
+
+__global__ void copy2d_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
+  int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+  if (i < rows && j < cols) dst[(size_t)i * ldd + j] = src[(size_t)i * lds + j];
+}
+
+// alpha = Kinv (y - mean0); one warp per row.  GP_prior.py:133
+__global__ void alpha_kernel(const double* __restrict__ Kinv, int ld, const double* __restrict__ y, double mean0, int n,
+                             double* __restrict__ alpha) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double a = 0.0;
+  for (int k = lane; k < n; k += 32) a = fma(Kinv[(size_t)row * ld + k], y[k] - mean0, a);
+  a = warp_sum(a);
+  if (lane == 0) alpha[row] = a;
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+extern "C" __attribute__((visibility("default"))) size_t mcpilco_gp_precompute_workspace_bytes(int N) {
+  size_t np = align_up((size_t)(N > 0 ? N : 1), NB);
+  return (2 * np * np + np * NB + (np / NB) * NB * NB) * sizeof(double) + 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_gp_covariance(const McpGpSpec* spec, const double* X1, int n1, const double* X2, int n2, int add_noise,
+                                     double* K, int ldk, void* stream) {
+  if (int e = check_spec(spec)) return e;
+  MCP_CHECK_ARG(X1 && K && n1 >= 0, "gp_covariance: null pointer or negative size");
+  if (!X2) { X2 = X1; n2 = n1; } else add_noise = 0;
+  MCP_CHECK_ARG(ldk >= n2, "gp_covariance: ldk %d < n2 %d", ldk, n2);
+  return launch_cov(*spec, X1, n1, X2, n2, add_noise, K, ldk, n2, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_gp_diag_covariance(const McpGpSpec* spec, const double* X, int n, double* diag, void* stream) {
+  if (int e = check_spec(spec)) return e;
+  if (n <= 0) return MCP_OK;
+  MCP_CHECK_ARG(X && diag, "gp_diag_covariance: null pointer");
+  MCP_DISPATCH_D(spec->D, (kdiag_kernel<DT><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(*spec, X, n, diag)));
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_gp_precompute(const McpGpSpec* spec, const double* Xtr, const double* y, int N, double* alpha, double* Kinv,
+                                     int ld, double* Lfac, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_spec(spec)) return e;
+  MCP_CHECK_ARG(N >= 1 && Xtr && y && alpha && Kinv && ld >= N, "gp_precompute: bad arguments (N=%d ld=%d)", N, ld);
+  MCP_CHECK_ARG(workspace && workspace_bytes >= mcpilco_gp_precompute_workspace_bytes(N), "gp_precompute: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np = (int)align_up((size_t)N, NB), nblk = np / NB;
+  double* Kp = (double*)align_up((size_t)workspace, 256);
+  double* W = Kp + (size_t)np * np;
+  double* P = W + (size_t)np * np;
+  double* invL = P + (size_t)np * NB;
+
+  // 1. K = k(X,X) + sigma_n2 I, padded to a multiple of the block size with an identity tail
+  MCP_CUDA(cudaMemsetAsync(Kp, 0, sizeof(double) * (size_t)np * np, st));
+  if (int e = launch_cov(*spec, Xtr, N, Xtr, N, 1, Kp, np, N, st)) return e;
+  if (np > N) { pad_identity_kernel<<<cdiv(np - N, 128), 128, 0, st>>>(Kp, np, N, np); MCP_LAUNCH_CHECK(); }
+
+  // 2. right-looking blocked Cholesky: factor diagonal block, L21 = A21 inv(L11)^T, A22 -= L21 L21^T
+  for (int kb = 0; kb < nblk; kb++) {
+    double* Akk = Kp + (size_t)kb * NB * np + kb * NB;
+    potrf_block_kernel<<<1, 256, 0, st>>>(Akk, np, invL + (size_t)kb * NB * NB);
+    MCP_LAUNCH_CHECK();
+    int m = np - (kb + 1) * NB;
+    if (m > 0) {
+      double* A21 = Akk + (size_t)NB * np;
+      if (int e = dgemm_nt(m, NB, NB, 1.0, A21, np, invL + (size_t)kb * NB * NB, NB, 0.0, P, NB, 0, 0, st)) return e;
+      copy2d_kernel<<<dim3(cdiv(NB, 32), cdiv(m, 8)), dim3(32, 8), 0, st>>>(P, NB, A21, np, m, NB);
+      MCP_LAUNCH_CHECK();
+      if (int e = dgemm_nt(m, m, NB, -1.0, P, NB, P, NB, 1.0, A21 + NB, np, 1, 0, st)) return e;
+    }
+  }
+  if (Lfac) {  // export L (lower; upper part of Kp still holds stale K entries, mask them)
+    lower_copy_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Lfac, ld, N);
+    MCP_LAUNCH_CHECK();
+  }
+
+  // 3. W = L^-T (upper), block column by block column:  W_ji = -(sum_k W_jk L_ik^T) inv(L_ii)^T,  W_ii = inv(L_ii)^T
+  MCP_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np, st));
+  for (int i = 0; i < nblk; i++) {
+    transpose_block_kernel<<<1, 256, 0, st>>>(invL + (size_t)i * NB * NB, NB, W + (size_t)i * NB * np + i * NB, np);
+    MCP_LAUNCH_CHECK();
+    if (i > 0) {
+      int mi = i * NB;
+      if (int e = dgemm_nt(mi, NB, mi, 1.0, W, np, Kp + (size_t)i * NB * np, np, 0.0, P, NB, 0, KF_A_UPPER, st)) return e;
+      if (int e = dgemm_nt(mi, NB, NB, -1.0, P, NB, invL + (size_t)i * NB * NB, NB, 0.0, W + i * NB, np, 0, 0, st)) return e;
+    }
+  }
+
+  // 4. K^-1 = W W^T (lower tiles, contraction trimmed to k >= max(row blocks)), mirrored into the output
+  if (int e = dgemm_nt(np, np, np, 1.0, W, np, W, np, 0.0, Kp, np, 1, KF_A_UPPER | KF_B_UPPER, st)) return e;
+  symmetrize_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Kinv, ld, N);
+  MCP_LAUNCH_CHECK();
+  if (ld > N) {  // keep the row padding finite (zero) for the tile loaders
+    MCP_CUDA(cudaMemset2DAsync(Kinv + N, sizeof(double) * ld, 0, sizeof(double) * (ld - N), N, st));
+  }
+  // 5. alpha = K^-1 (y - m)
+  alpha_kernel<<<cdiv(N, 8), 256, 0, st>>>(Kinv, ld, y, spec->mean0, N, alpha);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// posterior mean / variance and their Jacobians w.r.t. the test input (a3 + the per-step part of BPTT)
+// ------------------------------------------------------------------------------------------------
+namespace mcp {
+
+// One warp per particle.  Given V = K* K^-1 (row m), recompute k(x_m, xtr_n) and dk/dx on the fly and reduce
+//   mean = mean0 + sum_n alpha_n k_n            q = sum_n V_n k_n            var = scale (k** - q)
+//   dmean/dx = sum_n alpha_n dk_n/dx            dvar/dx = scale (dk**/dx - 2 sum_n V_n dk_n/dx)
+// (d(k^T Kinv k)/dx = 2 (Kinv k)^T dk/dx since Kinv is symmetric.)
+template <int DT, bool JAC>
+__global__ void __launch_bounds__(256) posterior_reduce_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
+                                                               int M, const double* __restrict__ Xtr, const double* __restrict__ alpha,
+                                                               int N, const double* __restrict__ V, int ldv, double var_scale,
+                                                               int E, int e, double* __restrict__ mean, double* __restrict__ var,
+                                                               double* __restrict__ jmean, double* __restrict__ jvar) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  double x[DT];
+  KFn<DT>::load(x, Xs + (size_t)m * s.D, s.D);
+  double mu = 0.0, q = 0.0, gm[DT], gq[DT];
+#pragma unroll
+  for (int j = 0; j < DT; j++) gm[j] = gq[j] = 0.0;
+  const double* v = V + (size_t)m * ldv;
+  for (int n = lane; n < N; n += 32) {
+    double y[DT];
+    KFn<DT>::load(y, Xtr + (size_t)n * s.D, s.D);
+    double a = alpha[n], vn = v[n];
+    if (JAC) {
+      double kv, dk[DT];
+      KFn<DT>::k_grad(s, x, y, kv, dk);
+      mu = fma(a, kv, mu);
+      q = fma(vn, kv, q);
+#pragma unroll
+      for (int j = 0; j < DT; j++) {
+        gm[j] = fma(a, dk[j], gm[j]);
+        gq[j] = fma(vn, dk[j], gq[j]);
+      }
+    } else {
+      double kv = KFn<DT>::k(s, x, y);
+      mu = fma(a, kv, mu);
+      q = fma(vn, kv, q);
+    }
+  }
+  mu = warp_sum(mu);
+  q = warp_sum(q);
+  if (JAC) {
+#pragma unroll
+    for (int j = 0; j < DT; j++) {
+      gm[j] = warp_sum(gm[j]);
+      gq[j] = warp_sum(gq[j]);
+    }
+  }
+  if (lane == 0) {
+    double kd, dkd[DT];
+    KFn<DT>::kdiag_grad(s, x, kd, dkd);
+    mean[(size_t)m * E + e] = s.mean0 + mu;
+    var[(size_t)m * E + e] = var_scale * (kd - q);
+    if (JAC) {
+#pragma unroll
+      for (int j = 0; j < DT; j++) {
+        if (j < s.D) {
+          jmean[((size_t)m * E + e) * s.D + j] = gm[j];
+          jvar[((size_t)m * E + e) * s.D + j] = var_scale * (dkd[j] - 2.0 * gq[j]);
+        }
+      }
+    }
+  }
+}
+
+static inline int ld16(int n) { return (n + 15) / 16 * 16; }
+
+// posterior of ONE GP for a chunk of particles through scratch [2 x Mc x ld16(N)]
+int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, double* mean, double* var, double* jmean,
+                       double* jvar, double* scratch, size_t scratch_doubles, cudaStream_t st) {
+  const int N = g.N, ldk = ld16(N);
+  MCP_CHECK_ARG(N >= 1 && g.Xtr && g.alpha && g.Kinv, "gp %d: null training data", e);
+  MCP_CHECK_ARG(g.ld_kinv >= N && g.ld_kinv % 2 == 0 && ((uintptr_t)g.Kinv % 16) == 0,
+                "gp %d: Kinv must be 16-byte aligned with an even leading dimension >= N (ld=%d N=%d)", e, g.ld_kinv, N);
+  size_t per = 2 * (size_t)ldk;
+  MCP_CHECK_ARG(scratch_doubles >= per, "posterior workspace too small for N=%d", N);
+  int Mc = (int)((scratch_doubles / per) < (size_t)M ? (scratch_doubles / per) : (size_t)M);
+  const bool jac = jmean != nullptr && jvar != nullptr;
+  for (int m0 = 0; m0 < M; m0 += Mc) {
+    int mc = (M - m0 < Mc) ? (M - m0) : Mc;
+    double* Ks = scratch;
+    double* V = scratch + (size_t)Mc * ldk;
+    const double* xs = Xs + (size_t)m0 * g.spec.D;
+    if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
+    if (int err = dgemm_nt(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, 0.0, V, ldk, 0, 0, st)) return err;
+    dim3 grid(cdiv(mc, 8));
+    double* jm = jac ? jmean + (size_t)m0 * E * g.spec.D : nullptr;
+    double* jv = jac ? jvar + (size_t)m0 * E * g.spec.D : nullptr;
+    if (jac) {
+      MCP_DISPATCH_D(g.spec.D, (posterior_reduce_kernel<DT, true><<<grid, 256, 0, st>>>(
+                                   g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E,
+                                   var + (size_t)m0 * E, jm, jv)));
+    } else {
+      MCP_DISPATCH_D(g.spec.D, (posterior_reduce_kernel<DT, false><<<grid, 256, 0, st>>>(
+                                   g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E,
+                                   var + (size_t)m0 * E, nullptr, nullptr)));
+    }
+    MCP_LAUNCH_CHECK();
+  }
+  return MCP_OK;
+}
+
+}  // namespace mcp
+
+extern "C" __attribute__((visibility("default"))) size_t mcpilco_gp_predict_workspace_bytes(int M, int Nmax) {
+  // scratch for K* and V = K* K^-1 of one particle chunk; capped at 2 GiB, at least 128 particles
+  size_t per = 2 * (size_t)mcp::ld16(Nmax > 0 ? Nmax : 1) * sizeof(double);
+  size_t want = per * (size_t)(M > 0 ? M : 1);
+  size_t cap = (size_t)2 << 30, floor_ = per * 128;
+  if (want > cap) want = cap;
+  if (want < floor_) want = floor_ < per * (size_t)(M > 0 ? M : 1) ? floor_ : per * (size_t)(M > 0 ? M : 1);
+  return want + 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_gp_predict(const McpGp* gps, int E, const double* Xs, int M, double* mean, double* var, double* jmean,
+                                  double* jvar, void* workspace, size_t workspace_bytes, void* stream) {
+  MCP_CHECK_ARG(gps && E >= 1 && E <= MCP_MAX_E, "gp_predict: bad E=%d", E);
+  MCP_CHECK_ARG(M >= 0 && (M == 0 || (Xs && mean && var)), "gp_predict: null pointer");
+  MCP_CHECK_ARG((jmean == nullptr) == (jvar == nullptr), "gp_predict: jmean and jvar must be given together");
+  if (M == 0) return MCP_OK;
+  MCP_CHECK_ARG(workspace && workspace_bytes >= 512, "gp_predict: workspace missing");
+  double* scratch = (double*)align_up((size_t)workspace, 256);
+  size_t doubles = (workspace_bytes - ((char*)scratch - (char*)workspace)) / sizeof(double);
+  for (int e = 0; e < E; e++) {
+    if (int err = check_spec(&gps[e].spec)) return err;
+    MCP_CHECK_ARG(gps[e].spec.D == gps[0].spec.D, "gp_predict: all GPs must share the input dimension");
+    if (int err = gp_posterior_chunk(gps[e], E, e, Xs, M, mean, var, jmean, jvar, scratch, doubles, (cudaStream_t)stream)) return err;
+  }
+  return MCP_OK;
+}

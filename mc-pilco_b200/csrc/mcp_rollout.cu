@@ -1,0 +1,638 @@
+// Particle rollout forward and the hand-written backprop-through-time.
+// Reference behaviour: policy_learning/MC_PILCO.py:615-674 (apply_policy), :808-906 (4PMS variant),
+// model_learning/Model_learning.py:210-229,670-718 (get_next_state), policy_learning/Policy.py:242-265,
+// 323-335,389-403 (policies), policy_learning/Cost_function.py:25-36,53-182 (costs), and the autograd
+// pass of MC_PILCO.py:522 which mcpilco_rollout_bwd replaces.
+#include "mcp_common.cuh"
+
+namespace mcp {
+
+int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, double* mean, double* var, double* jmean,
+                       double* jvar, double* scratch, size_t scratch_doubles, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers shared by forward and backward
+// ------------------------------------------------------------------------------------------------
+// policy feature j of the state seen by the policy (already divided by scale_factor)
+__device__ __forceinline__ double policy_feature(const McpPolicy& p, const double* __restrict__ x, int t, int j) {
+  double f;
+  if (p.kind == 1) {
+    if (j < p.n_na) f = x[p.na_idx[j]];
+    else if (j < p.n_na + p.n_a) f = cos(x[p.a_idx[j - p.n_na]]);
+    else f = sin(x[p.a_idx[j - p.n_na - p.n_a]]);
+  } else if (p.kind == 2) {
+    f = (j < p.Ds) ? x[j] : (p.target_traj[(size_t)t * p.Ds + (j - p.Ds)] - x[j - p.Ds]);
+  } else {
+    f = x[j];
+  }
+  return f * p.inv_scale[j];
+}
+
+__device__ __forceinline__ bool dropout_active(const McpPolicy& p, const McpNoise& nz) { return p.use_drop && nz.p_dropout > 0.0; }
+
+__device__ __forceinline__ bool keep_unit(const McpNoise& nz, int M, int nb, int t, int m, int b) {
+  if (nz.masks) return nz.masks[((size_t)t * M + m) * nb + b] != 0;
+  return rng_keep(nz.seed, nz.particle_offset + (uint64_t)m, t, b, nz.p_dropout);
+}
+
+__device__ __forceinline__ double cost_value(const McpCost& c, const double* __restrict__ x, int t, int Ds) {
+  if (c.kind == 1) {
+    double a = (fabs(x[c.idx[0]]) - c.target[0]) * c.inv_ls[0], b = (x[c.idx[1]] - c.target[1]) * c.inv_ls[1];
+    return 1.0 - exp(-(a * a) - b * b);
+  }
+  double d = 0.0;
+  for (int i = 0; i < c.n_idx; i++) {
+    double tg = (c.kind == 2) ? c.target_traj[(size_t)t * Ds + c.idx[i]] : c.target[i];
+    double r = (x[c.idx[i]] - tg) * c.inv_ls[i];
+    d = fma(r, r, d);
+  }
+  return (c.kind == 4) ? d : 1.0 - exp(-d);
+}
+
+// lam[j] += w * d cost / d x_j
+__device__ __forceinline__ void cost_grad_add(const McpCost& c, const double* __restrict__ x, int t, int Ds, double w, double* lam) {
+  if (c.kind == 1) {
+    double th = x[c.idx[0]];
+    double a = (fabs(th) - c.target[0]) * c.inv_ls[0], b = (x[c.idx[1]] - c.target[1]) * c.inv_ls[1];
+    double e = exp(-(a * a) - b * b);
+    double sg = (th > 0.0) ? 1.0 : ((th < 0.0) ? -1.0 : 0.0);
+    lam[c.idx[0]] += w * e * 2.0 * a * c.inv_ls[0] * sg;
+    lam[c.idx[1]] += w * e * 2.0 * b * c.inv_ls[1];
+    return;
+  }
+  double d = 0.0;
+  for (int i = 0; i < c.n_idx; i++) {
+    double tg = (c.kind == 2) ? c.target_traj[(size_t)t * Ds + c.idx[i]] : c.target[i];
+    double r = (x[c.idx[i]] - tg) * c.inv_ls[i];
+    d = fma(r, r, d);
+  }
+  double e = (c.kind == 4) ? 1.0 : exp(-d);
+  for (int i = 0; i < c.n_idx; i++) {
+    double tg = (c.kind == 2) ? c.target_traj[(size_t)t * Ds + c.idx[i]] : c.target[i];
+    lam[c.idx[i]] += w * e * 2.0 * (x[c.idx[i]] - tg) * c.inv_ls[i] * c.inv_ls[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernels
+// ------------------------------------------------------------------------------------------------
+// u_t = pi(pol_in_t) with dropout and squashing, one warp per particle; then the gp-input features
+// of (x_t, u_t).  Policy.py:242-265; Model_learning.py:670-683.
+__global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
+                                                         const __grid_constant__ McpNoise nz, int M, int t,
+                                                         const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
+                                                         double* __restrict__ u_t, double* __restrict__ Xs) {
+  __shared__ double s_il[MCP_MAX_DP];
+  __shared__ double s_z[8][MCP_MAX_DP];
+  __shared__ double s_u[8][MCP_MAX_DU];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + w;
+  if (threadIdx.x < pol.Dp) s_il[threadIdx.x] = exp(-pol.log_ls[threadIdx.x]);
+  if (m < M && lane < pol.Dp) s_z[w][lane] = policy_feature(pol, pol_in_t + (size_t)m * pol.Ds, t, lane);
+  __syncthreads();
+  if (m >= M) return;
+  const bool drop = dropout_active(pol, nz);
+  const double keep_scale = drop ? 1.0 / (1.0 - nz.p_dropout) : 1.0;
+  double a[MCP_MAX_DU];
+#pragma unroll
+  for (int k = 0; k < MCP_MAX_DU; k++) a[k] = 0.0;
+  for (int b = lane; b < pol.nb; b += 32) {
+    const double* c = pol.centers + (size_t)b * pol.Dp;
+    double d = 0.0;
+    for (int j = 0; j < pol.Dp; j++) {
+      double r = (s_z[w][j] - c[j]) * s_il[j];
+      d = fma(r, r, d);
+    }
+    double h = exp(-d);
+    if (drop) h = keep_unit(nz, M, pol.nb, t, m, b) ? h * keep_scale : 0.0;
+#pragma unroll
+    for (int k = 0; k < MCP_MAX_DU; k++)
+      if (k < pol.Du) a[k] = fma(pol.W[(size_t)k * pol.nb + b], h, a[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < MCP_MAX_DU; k++)
+    if (k < pol.Du) {
+      double v = warp_sum(a[k]);
+      if (lane == 0) {
+        if (pol.has_bias) v += pol.bias[k];
+        if (pol.squash) v = pol.u_max[k] * tanh(v / pol.u_max[k]);
+        u_t[(size_t)m * pol.Du + k] = v;
+        s_u[w][k] = v;
+      }
+    }
+  __syncwarp();
+  if (Xs != nullptr && lane < mdl.D) {
+    const double* x = x_t + (size_t)m * mdl.Ds;
+    int j = lane;
+    double f;
+    if (mdl.use_trig) {
+      if (j < mdl.n_na) f = x[mdl.na_idx[j]];
+      else if (j < mdl.n_na + mdl.n_a) f = sin(x[mdl.a_idx[j - mdl.n_na]]);
+      else if (j < mdl.n_na + 2 * mdl.n_a) f = cos(x[mdl.a_idx[j - mdl.n_na - mdl.n_a]]);
+      else f = s_u[w][j - mdl.n_na - 2 * mdl.n_a];
+    } else {
+      f = (j < mdl.Ds) ? x[j] : s_u[w][j - mdl.Ds];
+    }
+    Xs[(size_t)m * mdl.D + j] = f;
+  }
+}
+
+// delta = mean + sqrt(var) eps; integrate; checkpoint J = d(delta)/d(gp input); simulated measurement (4PMS).
+// Model_learning.py:685-718 / :471-493; MC_PILCO.py:878-899.
+__global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ McpModel mdl, const __grid_constant__ McpMeas ms,
+                                                        const __grid_constant__ McpNoise nz, int M, int t,
+                                                        const double* __restrict__ x_t, const double* __restrict__ mean,
+                                                        const double* __restrict__ var, const double* __restrict__ jmean,
+                                                        const double* __restrict__ jvar, double* __restrict__ x_n,
+                                                        double* __restrict__ jac_t, const double* __restrict__ polin_t,
+                                                        double* __restrict__ polin_n, double* __restrict__ nv) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int E = mdl.E, D = mdl.D, Ds = mdl.Ds;
+  const double* x = x_t + (size_t)m * Ds;
+  double* xn = x_n + (size_t)m * Ds;
+  if (mdl.kind == 1)
+    for (int j = 0; j < Ds; j++) xn[j] = 0.0;  // the reference starts from zeros (Model_learning.py:700)
+  for (int e = 0; e < E; e++) {
+    double mu = mean[(size_t)m * E + e], v = var[(size_t)m * E + e];
+    double delta = mu, coef = 0.0;
+    if (mdl.particle_pred) {
+      double eps = nz.eps ? nz.eps[((size_t)t * M + m) * E + e] : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_EPS, e);
+      double sd = sqrt(v);
+      delta = fma(sd, eps, mu);
+      coef = eps / (2.0 * sd);
+    }
+    if (jac_t) {
+      const double* jm = jmean + ((size_t)m * E + e) * D;
+      const double* jv = jvar + ((size_t)m * E + e) * D;
+      double* jo = jac_t + ((size_t)m * E + e) * D;
+      for (int d = 0; d < D; d++) jo[d] = fma(coef, jv[d], jm[d]);
+    }
+    if (mdl.kind == 1) {
+      int iv = mdl.vel_idx[e], ip = mdl.pos_idx[e];
+      xn[iv] = x[iv] + delta;
+      xn[ip] = x[ip] + mdl.T * x[iv] + 0.5 * mdl.T * delta;
+    } else {
+      xn[e] = x[e] + delta;
+    }
+  }
+  if (ms.enabled) {
+    // noisy positions, finite-difference velocity, first-order low-pass (MC_PILCO.py:881-899)
+    const double* pp = polin_t + (size_t)m * Ds;
+    double* pn = polin_n + (size_t)m * Ds;
+    for (int j = 0; j < Ds; j++) pn[j] = xn[j];
+    for (int i = 0; i < ms.n_pos; i++) {
+      int ip = ms.pos_idx[i], iv = ms.vel_idx[i];
+      double e = nz.meas_eps ? nz.meas_eps[((size_t)t * M + m) * ms.n_pos + i]
+                             : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_MEAS, i);
+      double np_old = pp[ip], mv_old = pp[iv];
+      double np_new = fma(ms.std_pos[i], e, xn[ip]);
+      double nv_old = nv[(size_t)m * ms.n_pos + i];
+      double nv_new = (np_new - np_old) / ms.T;
+      double mv_new = (ms.b0 * nv_new + ms.b1 * nv_old - ms.a1 * mv_old) / ms.a0;
+      nv[(size_t)m * ms.n_pos + i] = nv_new;
+      pn[ip] = np_new;
+      pn[iv] = mv_new;
+    }
+  }
+}
+
+__global__ void init_nv_kernel(const __grid_constant__ McpMeas ms, int M, int Ds, const double* __restrict__ x0, double* __restrict__ nv) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  for (int i = 0; i < ms.n_pos; i++) nv[(size_t)m * ms.n_pos + i] = x0[(size_t)m * Ds + ms.vel_idx[i]];
+}
+
+__global__ void __launch_bounds__(256) cost_kernel(const __grid_constant__ McpCost c, int M, int H, int Ds,
+                                                   const double* __restrict__ states, double* __restrict__ costs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * H) return;
+  int t = (int)(i / M);
+  costs[i] = cost_value(c, states + i * Ds, t, Ds);
+}
+
+// per time step: mean and M2 = sum (c - mean)^2 over particles (two passes, fixed summation order)
+__global__ void __launch_bounds__(256) cost_stats_kernel(int M, const double* __restrict__ costs, double* __restrict__ stats) {
+  __shared__ double red[8];
+  __shared__ double s_mean;
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const double* c = costs + (size_t)t * M;
+  double a = 0.0;
+  for (int m = tid; m < M; m += 256) a += c[m];
+  a = warp_sum(a);
+  if ((tid & 31) == 0) red[tid >> 5] = a;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; i++) s += red[i];
+    s_mean = s / M;
+  }
+  __syncthreads();
+  double mean = s_mean, q = 0.0;
+  for (int m = tid; m < M; m += 256) {
+    double d = c[m] - mean;
+    q = fma(d, d, q);
+  }
+  q = warp_sum(q);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = q;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; i++) s += red[i];
+    stats[2 * t] = mean;
+    stats[2 * t + 1] = s;
+  }
+}
+
+// Expected_cost.forward: sum_t mean_t and sum_t unbiased std_t.  Cost_function.py:33-36
+__global__ void cost_final_kernel(int M, int H, const double* __restrict__ stats, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double a = 0.0, b = 0.0;
+  for (int t = 0; t < H; t++) {
+    a += stats[2 * t];
+    b += sqrt(stats[2 * t + 1] / (double)(M - 1));
+  }
+  out[0] = a;
+  out[1] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: reverse sweep over the horizon, one CTA per particle (grid-strided), thread <-> basis function
+// ------------------------------------------------------------------------------------------------
+template <int DPT, int DUT>
+__global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant__ McpRollout r, const __grid_constant__ McpRolloutGrad g,
+                                                           double* __restrict__ partials, double* __restrict__ g_x0) {
+  const McpModel& mdl = r.model;
+  const McpPolicy& pol = r.policy;
+  const McpMeas& ms = r.meas;
+  const int M = r.M, H = r.H, Ds = mdl.Ds, Du = mdl.Du, E = mdl.E, D = mdl.D, nb = pol.nb, Dp = pol.Dp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int b = tid;
+  const bool has_b = b < nb;
+
+  __shared__ double s_il[MCP_MAX_DP], s_z[MCP_MAX_DP], s_lz[MCP_MAX_DP], s_glz[MCP_MAX_DP];
+  __shared__ double s_lam[MCP_MAX_DS], s_lnext[MCP_MAX_DS], s_la[MCP_MAX_DU], s_gbias[MCP_MAX_DU];
+  __shared__ double s_lnv[MCP_MAX_E], s_lmv[MCP_MAX_E], s_lnp[MCP_MAX_E];
+  __shared__ double s_red[16][MCP_MAX_DP];
+  __shared__ int s_active;
+
+  if (tid < Dp) { s_il[tid] = exp(-pol.log_ls[tid]); s_glz[tid] = 0.0; }
+  if (tid < MCP_MAX_DU) s_gbias[tid] = 0.0;
+  double cb[DPT], gc[DPT], wb[DUT], gw[DUT];
+#pragma unroll
+  for (int j = 0; j < DPT; j++) { cb[j] = (has_b && j < Dp) ? pol.centers[(size_t)b * Dp + j] : 0.0; gc[j] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < DUT; k++) { wb[k] = (has_b && k < Du) ? pol.W[(size_t)k * nb + b] : 0.0; gw[k] = 0.0; }
+  const bool drop = dropout_active(pol, r.noise);
+  const double keep_scale = drop ? 1.0 / (1.0 - r.noise.p_dropout) : 1.0;
+  const double cost_w = (r.cost.kind != 0 && g.grad_states == nullptr) ? g.grad_cost / (double)M : 0.0;
+  const double* polin = (ms.enabled && r.pol_in) ? r.pol_in : r.states;
+  __syncthreads();
+
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    if (tid == 0) {
+      for (int j = 0; j < Ds; j++) s_lnext[j] = 0.0;
+      for (int i = 0; i < MCP_MAX_E; i++) s_lnv[i] = s_lmv[i] = s_lnp[i] = 0.0;
+    }
+    for (int t = H - 1; t >= 0; t--) {
+      const double* x = r.states + ((size_t)t * M + m) * Ds;
+      const double* px = polin + ((size_t)t * M + m) * Ds;
+      const double* u = r.inputs + ((size_t)t * M + m) * Du;
+      // ---- stage A: adjoint of x_t from cost and from the model step t -> t+1; adjoint of u_t ----
+      if (tid == 0) {
+        double lam[MCP_MAX_DS], lu[MCP_MAX_DU];
+        for (int j = 0; j < Ds; j++) lam[j] = g.grad_states ? g.grad_states[((size_t)t * M + m) * Ds + j] : 0.0;
+        for (int k = 0; k < Du; k++) lu[k] = g.grad_inputs ? g.grad_inputs[((size_t)t * M + m) * Du + k] : 0.0;
+        if (cost_w != 0.0) cost_grad_add(r.cost, x, t, Ds, cost_w, lam);
+        if (t < H - 1) {
+          const double* J = r.jac + ((size_t)t * M + m) * E * D;
+          double lx[MCP_MAX_D];
+          for (int d = 0; d < D; d++) lx[d] = 0.0;
+          for (int e = 0; e < E; e++) {
+            double ld;
+            if (mdl.kind == 1) {
+              int iv = mdl.vel_idx[e], ip = mdl.pos_idx[e];
+              ld = s_lnext[iv] + 0.5 * mdl.T * s_lnext[ip];
+              lam[iv] += s_lnext[iv] + mdl.T * s_lnext[ip];
+              lam[ip] += s_lnext[ip];
+            } else {
+              ld = s_lnext[e];
+              lam[e] += s_lnext[e];
+            }
+            for (int d = 0; d < D; d++) lx[d] = fma(ld, J[(size_t)e * D + d], lx[d]);
+          }
+          if (mdl.use_trig) {
+            for (int i = 0; i < mdl.n_na; i++) lam[mdl.na_idx[i]] += lx[i];
+            for (int i = 0; i < mdl.n_a; i++) {
+              double sn, cs;
+              sincos(x[mdl.a_idx[i]], &sn, &cs);
+              lam[mdl.a_idx[i]] += lx[mdl.n_na + i] * cs - lx[mdl.n_na + mdl.n_a + i] * sn;
+            }
+            for (int k = 0; k < Du; k++) lu[k] += lx[mdl.n_na + 2 * mdl.n_a + k];
+          } else {
+            for (int j = 0; j < Ds; j++) lam[j] += lx[j];
+            for (int k = 0; k < Du; k++) lu[k] += lx[Ds + k];
+          }
+        }
+        int act = 0;
+        for (int k = 0; k < Du; k++) {
+          double la = lu[k];
+          if (pol.squash) { double q = u[k] / pol.u_max[k]; la *= (1.0 - q * q); }
+          s_la[k] = la;
+          s_gbias[k] += la;
+          act |= (la != 0.0);
+        }
+        for (int j = 0; j < Ds; j++) s_lam[j] = lam[j];
+        s_active = act;
+      }
+      if (tid < Dp) s_z[tid] = policy_feature(pol, px, t, tid);
+      __syncthreads();
+      // ---- stage B: policy backward, thread b owns basis function b ----
+      if (s_active) {
+        double ld_b = 0.0;
+        if (has_b) {
+          double d = 0.0;
+#pragma unroll
+          for (int j = 0; j < DPT; j++)
+            if (j < Dp) { double q = (s_z[j] - cb[j]) * s_il[j]; d = fma(q, q, d); }
+          double h = exp(-d);
+          if (drop) h = keep_unit(r.noise, M, nb, t, m, b) ? h * keep_scale : 0.0;
+          double lh = 0.0;
+#pragma unroll
+          for (int k = 0; k < DUT; k++)
+            if (k < Du) { gw[k] = fma(s_la[k], h, gw[k]); lh = fma(s_la[k], wb[k], lh); }
+          ld_b = -h * lh;
+        }
+#pragma unroll
+        for (int j = 0; j < DPT; j++) {
+          if (j < Dp) {
+            double cz = ld_b * 2.0 * (s_z[j] - cb[j]) * s_il[j] * s_il[j];  // d/dz_j ; d/dc_bj = -cz
+            gc[j] -= cz;
+            double v = warp_sum(cz);
+            if (lane == 0) s_red[warp][j] = v;
+          }
+        }
+        __syncthreads();
+        if (tid < Dp) {
+          double v = 0.0;
+          for (int w2 = 0; w2 < nwarp; w2++) v += s_red[w2][tid];
+          s_lz[tid] = v;
+          s_glz[tid] -= s_z[tid] * v;  // log-lengthscale gradient, first half (see below)
+        }
+        __syncthreads();
+      }
+      // ---- stage C: adjoint of the policy input -> adjoint of x_t (through the measurement model if any) ----
+      if (tid == 0) {
+        double lp[MCP_MAX_DS];
+        for (int j = 0; j < Ds; j++) lp[j] = 0.0;
+        if (s_active) {
+          if (pol.kind == 1) {
+            for (int i = 0; i < pol.n_na; i++) lp[pol.na_idx[i]] += s_lz[i] * pol.inv_scale[i];
+            for (int i = 0; i < pol.n_a; i++) {
+              double sn, cs;
+              sincos(px[pol.a_idx[i]], &sn, &cs);
+              lp[pol.a_idx[i]] += -s_lz[pol.n_na + i] * pol.inv_scale[pol.n_na + i] * sn +
+                                  s_lz[pol.n_na + pol.n_a + i] * pol.inv_scale[pol.n_na + pol.n_a + i] * cs;
+            }
+          } else if (pol.kind == 2) {
+            for (int j = 0; j < Ds; j++) lp[j] += s_lz[j] * pol.inv_scale[j] - s_lz[Ds + j] * pol.inv_scale[Ds + j];
+          } else {
+            for (int j = 0; j < Ds; j++) lp[j] += s_lz[j] * pol.inv_scale[j];
+          }
+        }
+        if (ms.enabled) {
+          for (int i = 0; i < ms.n_pos; i++) {
+            int ip = ms.pos_idx[i], iv = ms.vel_idx[i];
+            double lnp = s_lnp[i] + lp[ip], lmv = s_lmv[i] + lp[iv], lnv = s_lnv[i];
+            lp[ip] = 0.0;
+            lp[iv] = 0.0;
+            if (t > 0) {
+              lnv += ms.b0 / ms.a0 * lmv;
+              s_lnv[i] = ms.b1 / ms.a0 * lmv;   // carried to nv_{t-1}
+              s_lmv[i] = -ms.a1 / ms.a0 * lmv;  // carried to mv_{t-1}
+              lnp += lnv / ms.T;
+              s_lnp[i] = -lnv / ms.T;           // carried to np_{t-1}
+              s_lam[ip] += lnp;
+            } else {
+              s_lam[ip] += lnp;
+              s_lam[iv] += lnv + lmv;
+            }
+          }
+        }
+        for (int j = 0; j < Ds; j++) { s_lam[j] += lp[j]; s_lnext[j] = s_lam[j]; }
+      }
+      __syncthreads();
+    }
+    if (g_x0 != nullptr && tid < Ds) g_x0[(size_t)m * Ds + tid] = s_lnext[tid];
+    __syncthreads();
+  }
+
+  // ---- per-CTA partial gradients: [g_log_ls (Dp) | g_centers (nb*Dp) | g_W (Du*nb) | g_bias (Du)] ----
+  // d/dlog l_j of ((z_j-c_bj)/l_j)^2 = -2 ((z_j-c_bj)/l_j)^2, hence
+  //   g_logls_j = sum_steps sum_b [d/dc_bj contribution] (z_j - c_bj) = -sum_steps z_j lz_j - sum_b c_bj g_c[b][j]
+  double* P = partials + (size_t)blockIdx.x * (Dp + (size_t)nb * Dp + (size_t)Du * nb + Du);
+#pragma unroll
+  for (int j = 0; j < DPT; j++) {
+    if (j < Dp) {
+      double v = warp_sum(cb[j] * gc[j]);
+      if (lane == 0) s_red[warp][j] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < Dp) {
+    double v = 0.0;
+    for (int w2 = 0; w2 < nwarp; w2++) v += s_red[w2][tid];
+    P[tid] = s_glz[tid] - v;
+  }
+  if (has_b) {
+#pragma unroll
+    for (int j = 0; j < DPT; j++)
+      if (j < Dp) P[Dp + (size_t)b * Dp + j] = gc[j];
+#pragma unroll
+    for (int k = 0; k < DUT; k++)
+      if (k < Du) P[Dp + (size_t)nb * Dp + (size_t)k * nb + b] = gw[k];
+  }
+  if (tid < Du) P[Dp + (size_t)nb * Dp + (size_t)Du * nb + tid] = s_gbias[tid];
+}
+
+// out[i] = sum over CTAs of partials[cta][i] (fixed order -> bit-stable)
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int ncta, int n, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int c = 0; c < ncta; c++) a += partials[(size_t)c * n + i];
+  out[i] = a;
+}
+
+__global__ void scatter_grads_kernel(const double* __restrict__ flat, int Dp, int nb, int Du, double* g_log_ls, double* g_centers,
+                                     double* g_W, double* g_bias) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = Dp + nb * Dp + Du * nb + Du;
+  if (i >= n) return;
+  double v = flat[i];
+  if (i < Dp) { if (g_log_ls) g_log_ls[i] = v; return; }
+  i -= Dp;
+  if (i < nb * Dp) { if (g_centers) g_centers[i] = v; return; }
+  i -= nb * Dp;
+  if (i < Du * nb) { if (g_W) g_W[i] = v; return; }
+  i -= Du * nb;
+  if (g_bias) g_bias[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+  double *Xs, *mean, *var, *jmean, *jvar, *nv, *stats, *partials, *flat, *scratch;
+  size_t scratch_doubles;
+  int bwd_ctas;
+};
+
+static int bwd_grid(int M) {
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int g = sms * 2;
+  return M < g ? M : g;
+}
+
+static size_t fixed_doubles(int M, int H, int E, int D, int nb, int Dp, int Du, int npos, int ctas) {
+  size_t nparam = (size_t)Dp + (size_t)nb * Dp + (size_t)Du * nb + Du;
+  size_t n = 0;
+  n += align_up((size_t)M * D, 32);          // Xs
+  n += 2 * align_up((size_t)M * E, 32);      // mean, var
+  n += 2 * align_up((size_t)M * E * D, 32);  // jmean, jvar
+  n += align_up((size_t)M * (npos > 0 ? npos : 1), 32);
+  n += align_up((size_t)2 * H, 32);
+  n += align_up((size_t)ctas * nparam, 32);
+  n += align_up(nparam, 32);
+  return n;
+}
+
+static int carve(const McpRollout* r, Workspace& w) {
+  const int M = r->M, H = r->H, E = r->model.E, D = r->model.D;
+  const int nb = r->policy.nb, Dp = r->policy.Dp, Du = r->policy.Du, npos = r->meas.enabled ? r->meas.n_pos : 0;
+  MCP_CHECK_ARG(r->workspace != nullptr, "rollout: workspace missing");
+  w.bwd_ctas = bwd_grid(M);
+  double* p = (double*)align_up((size_t)r->workspace, 256);
+  size_t avail = (r->workspace_bytes - ((char*)p - (char*)r->workspace)) / sizeof(double);
+  size_t need = fixed_doubles(M, H, E, D, nb, Dp, Du, npos, w.bwd_ctas);
+  MCP_CHECK_ARG(avail > need + 1024, "rollout: workspace too small (%zu doubles, need > %zu)", avail, need + 1024);
+  size_t nparam = (size_t)Dp + (size_t)nb * Dp + (size_t)Du * nb + Du;
+  w.Xs = p; p += align_up((size_t)M * D, 32);
+  w.mean = p; p += align_up((size_t)M * E, 32);
+  w.var = p; p += align_up((size_t)M * E, 32);
+  w.jmean = p; p += align_up((size_t)M * E * D, 32);
+  w.jvar = p; p += align_up((size_t)M * E * D, 32);
+  w.nv = p; p += align_up((size_t)M * (npos > 0 ? npos : 1), 32);
+  w.stats = p; p += align_up((size_t)2 * H, 32);
+  w.partials = p; p += align_up((size_t)w.bwd_ctas * nparam, 32);
+  w.flat = p; p += align_up(nparam, 32);
+  w.scratch = p;
+  w.scratch_doubles = avail - need;
+  return MCP_OK;
+}
+
+static int check_rollout(const McpRollout* r) {
+  MCP_CHECK_ARG(r != nullptr, "null rollout descriptor");
+  const McpModel& m = r->model;
+  const McpPolicy& p = r->policy;
+  MCP_CHECK_ARG(r->M >= 1 && r->H >= 1, "rollout: M=%d H=%d", r->M, r->H);
+  MCP_CHECK_ARG(m.Ds >= 1 && m.Ds <= MCP_MAX_DS && m.Du >= 1 && m.Du <= MCP_MAX_DU && m.E >= 1 && m.E <= MCP_MAX_E &&
+                    m.D >= 1 && m.D <= MCP_MAX_D, "rollout: model dims out of range (Ds=%d Du=%d E=%d D=%d)", m.Ds, m.Du, m.E, m.D);
+  int dfeat = m.use_trig ? m.n_na + 2 * m.n_a + m.Du : m.Ds + m.Du;
+  MCP_CHECK_ARG(dfeat == m.D, "rollout: gp-input dimension %d does not match the feature map (%d)", m.D, dfeat);
+  MCP_CHECK_ARG(m.kind == 1 || m.E == m.Ds, "rollout: delta-state model needs E == Ds");
+  MCP_CHECK_ARG(p.nb >= 1 && p.nb <= 512 && p.Dp >= 1 && p.Dp <= MCP_MAX_DP && p.Du == m.Du && p.Ds == m.Ds,
+                "rollout: policy dims out of range (nb=%d Dp=%d Du=%d Ds=%d)", p.nb, p.Dp, p.Du, p.Ds);
+  int dp = p.kind == 1 ? p.n_na + 2 * p.n_a : (p.kind == 2 ? 2 * p.Ds : p.Ds);
+  MCP_CHECK_ARG(dp == p.Dp, "rollout: policy feature dimension %d does not match kind %d (%d)", p.Dp, p.kind, dp);
+  MCP_CHECK_ARG(p.log_ls && p.centers && p.W && (!p.has_bias || p.bias) && (p.kind != 2 || p.target_traj), "rollout: null policy tensor");
+  MCP_CHECK_ARG(r->gps && r->x0 && r->states && r->inputs, "rollout: null tensor");
+  MCP_CHECK_ARG(!r->need_grad || r->H == 1 || r->jac, "rollout: need_grad requires the jac checkpoint buffer");
+  MCP_CHECK_ARG(!r->meas.enabled || r->pol_in, "rollout: the measurement model needs pol_in");
+  MCP_CHECK_ARG(r->cost.kind == 0 || r->costs, "rollout: fused cost needs the costs buffer");
+  MCP_CHECK_ARG(r->cost.kind != 2 || r->cost.target_traj, "rollout: trajectory cost needs target_traj");
+  MCP_CHECK_ARG(r->noise.p_dropout >= 0.0 && r->noise.p_dropout < 1.0, "rollout: p_dropout outside [0,1)");
+  for (int e = 0; e < m.E; e++) MCP_CHECK_ARG(r->gps[e].spec.D == m.D, "rollout: gp %d input dim %d != %d", e, r->gps[e].spec.D, m.D);
+  return MCP_OK;
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+extern "C" __attribute__((visibility("default"))) size_t mcpilco_rollout_workspace_bytes(int M, int H, int E, int D, int Nmax, int nb, int Dp, int Du) {
+  size_t fixed = fixed_doubles(M, H, E, D, nb, Dp, Du, E, bwd_grid(M)) * sizeof(double);
+  return fixed + mcpilco_gp_predict_workspace_bytes(M, Nmax) + 16384;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const McpRollout* r, void* stream) {
+  if (int e = check_rollout(r)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  if (int e = carve(r, w)) return e;
+  const int M = r->M, H = r->H, Ds = r->model.Ds, Du = r->model.Du, E = r->model.E, D = r->model.D;
+  const bool meas = r->meas.enabled != 0;
+  MCP_CUDA(cudaMemcpyAsync(r->states, r->x0, sizeof(double) * (size_t)M * Ds, cudaMemcpyDeviceToDevice, st));
+  if (meas) {
+    MCP_CUDA(cudaMemcpyAsync(r->pol_in, r->x0, sizeof(double) * (size_t)M * Ds, cudaMemcpyDeviceToDevice, st));
+    init_nv_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->meas, M, Ds, r->x0, w.nv);
+    MCP_LAUNCH_CHECK();
+  }
+  for (int t = 0; t < H; t++) {
+    const double* x_t = r->states + (size_t)t * M * Ds;
+    const double* p_t = meas ? r->pol_in + (size_t)t * M * Ds : x_t;
+    policy_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(r->policy, r->model, r->noise, M, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
+                                                  t < H - 1 ? w.Xs : nullptr);
+    MCP_LAUNCH_CHECK();
+    if (t == H - 1) break;
+    for (int e = 0; e < E; e++) {
+      if (int err = gp_posterior_chunk(r->gps[e], E, e, w.Xs, M, w.mean, w.var, r->need_grad ? w.jmean : nullptr,
+                                       r->need_grad ? w.jvar : nullptr, w.scratch, w.scratch_doubles, st))
+        return err;
+    }
+    integrate_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->model, r->meas, r->noise, M, t, x_t, w.mean, w.var, w.jmean, w.jvar,
+                                                   r->states + (size_t)(t + 1) * M * Ds,
+                                                   r->need_grad ? r->jac + (size_t)t * M * E * D : nullptr, p_t,
+                                                   meas ? r->pol_in + (size_t)(t + 1) * M * Ds : nullptr, w.nv);
+    MCP_LAUNCH_CHECK();
+  }
+  if (r->cost.kind != 0) {
+    size_t n = (size_t)M * H;
+    cost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r->cost, M, H, Ds, r->states, r->costs);
+    MCP_LAUNCH_CHECK();
+    cost_stats_kernel<<<H, 256, 0, st>>>(M, r->costs, w.stats);
+    MCP_LAUNCH_CHECK();
+    if (r->cost_out) {
+      cost_final_kernel<<<1, 32, 0, st>>>(M, H, w.stats, r->cost_out);
+      MCP_LAUNCH_CHECK();
+    }
+  }
+  return MCP_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_bwd(const McpRollout* r, const McpRolloutGrad* g, void* stream) {
+  if (int e = check_rollout(r)) return e;
+  MCP_CHECK_ARG(g != nullptr, "rollout_bwd: null gradient descriptor");
+  MCP_CHECK_ARG(r->H == 1 || r->jac, "rollout_bwd: forward was run without need_grad");
+  MCP_CHECK_ARG(g->grad_states || r->cost.kind != 0, "rollout_bwd: neither grad_states nor a fused cost");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  if (int e = carve(r, w)) return e;
+  const int nb = r->policy.nb, Dp = r->policy.Dp, Du = r->policy.Du;
+  const int nparam = Dp + nb * Dp + Du * nb + Du;
+  const int threads = (nb + 31) / 32 * 32;
+#define MCP_BWD(DPT, DUT) rollout_bwd_kernel<DPT, DUT><<<w.bwd_ctas, threads, 0, st>>>(*r, *g, w.partials, g->g_x0)
+  if (Dp <= 8) { if (Du <= 2) MCP_BWD(8, 2); else MCP_BWD(8, 8); }
+  else if (Dp <= 16) { if (Du <= 2) MCP_BWD(16, 2); else MCP_BWD(16, 8); }
+  else { if (Du <= 2) MCP_BWD(32, 2); else MCP_BWD(32, 8); }
+#undef MCP_BWD
+  MCP_LAUNCH_CHECK();
+  reduce_partials_kernel<<<cdiv(nparam, 128), 128, 0, st>>>(w.partials, w.bwd_ctas, nparam, w.flat);
+  MCP_LAUNCH_CHECK();
+  scatter_grads_kernel<<<cdiv(nparam, 128), 128, 0, st>>>(w.flat, Dp, nb, Du, g->g_log_ls, g->g_centers, g->g_W, g->g_bias);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
