@@ -1,0 +1,100 @@
+"""CPU: the shared library loads, exports every symbol include/mcpilco_b200.h declares, and the ctypes mirrors have the
+library's struct layout.  No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    from mcpilco_b200 import _build, _native
+    _build.build()
+    return _native
+
+
+def test_header_symbols_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "mcpilco_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mcpilco_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(native.SYMBOLS), declared ^ set(native.SYMBOLS)
+    L = C.CDLL(native.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_abi_version_and_struct_layout(native):
+    L = native.lib()  # raises on ABI or struct-size mismatch
+    assert L.mcpilco_abi_version() == native.ABI_VERSION
+    assert L.mcpilco_launch_count(0) == 0
+
+
+def test_header_limits_match_binding(native):
+    hdr = open(os.path.join(ROOT, "include", "mcpilco_b200.h")).read()
+    for name, val in (("MCP_MAX_D", native.MAX_D), ("MCP_MAX_DS", native.MAX_DS), ("MCP_MAX_DU", native.MAX_DU),
+                      ("MCP_MAX_E", native.MAX_E), ("MCP_MAX_DP", native.MAX_DP), ("MCP_MAX_POLY", native.MAX_POLY),
+                      ("MCP_MAX_DEG", native.MAX_DEG), ("MCP_ABI_VERSION", native.ABI_VERSION)):
+        assert int(re.search(r"#define\s+%s\s+(\d+)" % name, hdr).group(1)) == val
+
+
+def test_no_device_is_a_loud_error(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = native.lib()
+    sm = C.c_int(0)
+    assert L.mcpilco_device_info(C.byref(sm), None, None) == -2  # MCP_E_CUDA
+    assert b"failed" in L.mcpilco_last_error()
+    from mcpilco_b200 import _ops, _pack
+    spec = _pack.spec_from_dict({"D": 2, "log_ls": [0.0, 0.0], "sigma_n": 0.1})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _ops.gp_covariance(spec, torch.zeros(3, 2, dtype=torch.float64))
+
+
+def test_spec_flattening_matches_oracle_closed_form():
+    """_pack turns reference-style log-parameters into the closed form k(x,y) the kernels evaluate; check that closed form
+    (evaluated here in numpy from the packed struct) against the oracle's reference-ordered computation."""
+    import torch
+    from mcpilco_b200 import _native as N, _pack as P
+    from oracle import mcpilco_oracle as O
+    rs = np.random.RandomState(0)
+    D = 6
+    log_ls = rs.randn(D)
+    mpk = [np.exp(rs.randn(D + 1) - 3), np.exp(rs.randn(2 * D) - 3), np.exp(rs.randn(3 * D) - 3)]
+    s = P.spec_from_dict({"D": D, "log_ls": log_ls, "lambda": 1.7, "mean": 0.3, "mpk": mpk, "sigma_n": 0.05, "sigma_n_num": 0.01})
+    so = O.make_spec(D, log_ls=log_ls, log_lambda=np.log(1.7), mean=0.3, mpk_log_pars=[np.log(w) for w in mpk], sigma_n=0.05,
+                     sigma_n_num=0.01)
+    X1, X2 = rs.randn(5, D), rs.randn(7, D)
+
+    def k_packed(x, y):
+        v = 0.0
+        if s.has_se:
+            v += s.lambda_ * np.exp(-sum(((x[j] - y[j]) * s.inv_ls[j]) ** 2 for j in range(D)))
+        for p in range(s.n_poly):
+            pr = 1.0
+            for f in range(N.MAX_DEG):
+                pr *= sum(s.poly_w2[p][f][j] * x[j] * y[j] for j in range(D)) + s.poly_w2[p][f][N.MAX_D]
+            v += pr
+        return v
+    K = np.array([[k_packed(a, b) for b in X2] for a in X1])
+    Ko = O.gp_cov(so, torch.tensor(X1), torch.tensor(X2)).numpy()
+    np.testing.assert_allclose(K, Ko, rtol=1e-12)
+    assert abs(s.sigma_n2 - float(O.sigma_n2(so))) < 1e-16 and s.mean0 == 0.3 and list(s.poly_deg) == [1, 2, 3]
+
+
+def test_struct_builders_validate():
+    from mcpilco_b200 import _pack as P
+    with pytest.raises(ValueError):
+        P.new_gp_spec(0)
+    with pytest.raises(ValueError):
+        P.add_mpk(P.new_gp_spec(4), np.arange(4), 2, False, np.zeros(5))
+    with pytest.raises(ValueError):
+        P.model_struct("speed", 4, 1, 2, angle=[2], not_angle=[0, 1, 3], vel=[1], pos=[0, 2], T=0.05)
+    m = P.model_struct("speed", 4, 1, 2, angle=[2], not_angle=[0, 1, 3], vel=[1, 3], pos=[0, 2], T=0.05)
+    assert (m.D, m.n_na, m.n_a, m.kind, m.use_trig) == (6, 3, 1, 1, 1)
+    ms = P.meas_struct([0, 2], [1, 3], [3e-3, 3e-3], 0.5, 1 / 30)
+    assert abs(ms.b0 - 0.5) < 1e-15 and abs(ms.a1) < 1e-15 and ms.enabled == 1

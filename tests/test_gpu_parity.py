@@ -1,0 +1,284 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors produced by the reference and
+against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): posterior mean/var and rollout cost 1e-5 relative, policy
+gradients 1e-4 relative (fp64 mode).  Where the check is formula-level (the reference's own alpha/K^-1
+are fed in) the tolerance is tightened to rounding level.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as Hh
+import scenarios
+from oracle import mcpilco_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_VAL = 1e-5   # north-star tolerance for mean / var / cost
+REL_GRAD = 1e-4  # north-star tolerance for policy gradients
+
+
+@pytest.fixture(scope="module")
+def nh():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import native_helpers
+    return native_helpers
+
+
+def close(a, b, rtol, atol=0.0):
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    np.testing.assert_allclose(a, np.asarray(b), rtol=rtol, atol=atol)
+
+
+def relmax(a, b):
+    """max |a-b| / max |b|: the norm-wise relative error used for gradient tensors."""
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    b = np.asarray(b)
+    return float(np.abs(a.reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_covariance(nh, name):
+    from mcpilco_b200 import _ops as ops
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    X, Xs = nh.G(sc["X"]), nh.G(g["Xs"])
+    for e, sp in enumerate(nh.native_specs(sc)):
+        close(ops.gp_covariance(sp, Xs, X), g[f"Kss_{e}"], 1e-12, 1e-15)
+        close(ops.gp_covariance(sp, X, None, add_noise=True), g[f"Knoise_{e}"], 1e-12, 1e-15)
+        close(ops.gp_diag_covariance(sp, Xs), g[f"kdiag_{e}"], 1e-12)
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_precompute(nh, name):
+    from mcpilco_b200 import _ops as ops
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    X = nh.G(sc["X"])
+    for e, sp in enumerate(nh.native_specs(sc)):
+        alpha, Kinv, Lf = ops.gp_precompute(sp, X, nh.G(sc["Y"][:, e:e + 1]), want_L=True)
+        # conditioning-limited (cond(K) ~ 1e5..1e6): same bound the oracle is held to against the reference
+        close(Kinv, g[f"Kinv_{e}"], 1e-7, 1e-7 * np.abs(g[f"Kinv_{e}"]).max())
+        close(alpha, g[f"alpha_{e}"], 1e-7, 1e-7 * np.abs(g[f"alpha_{e}"]).max())
+        Kn = torch.tensor(g[f"Knoise_{e}"], dtype=torch.float64, device=X.device)
+        close(Lf @ Lf.t(), g[f"Knoise_{e}"], 1e-12, 1e-14)                      # L L^T = K
+        close(Kinv @ Kn, np.eye(X.shape[0]), 0, 1e-8)                            # K^-1 K = I
+        assert torch.equal(Kinv, Kinv.t())                                      # exactly symmetric
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_posterior_formula(nh, name):
+    """Reference alpha / K^-1 in, posterior out: formula parity at rounding level."""
+    from mcpilco_b200 import _ops as ops
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    gps = nh.native_fit(sc, golden=g)
+    mean, var = ops.gp_predict(gps, nh.G(g["Xs"]))
+    for e in range(sc["E"]):
+        close(mean[:, e:e + 1], g[f"pmean_{e}"], 1e-10, 1e-13)
+        close(var[:, e], g[f"pvar_{e}"], 1e-8, 1e-13)
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_posterior_end_to_end(nh, name):
+    """Own precompute + own posterior vs the reference, at the stated tolerance."""
+    from mcpilco_b200 import _ops as ops
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    mean, var = ops.gp_predict(nh.native_fit(sc), nh.G(g["Xs"]))
+    for e in range(sc["E"]):
+        close(mean[:, e:e + 1], g[f"pmean_{e}"], REL_VAL, 1e-9)
+        close(var[:, e], g[f"pvar_{e}"], REL_VAL)
+
+
+@pytest.mark.parametrize("name", ["c1", "c4", "delta"])
+def test_posterior_jacobian(nh, name):
+    """d mean / d x and d var / d x against autograd through the oracle."""
+    from mcpilco_b200 import _ops as ops
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    gps = nh.native_fit(sc, golden=g)
+    Xs = nh.G(g["Xs"])
+    _, _, jm, jv = ops.gp_predict(gps, Xs, jac=True)
+    X = Hh.T(sc["X"])
+    for e, sp in enumerate(Hh.oracle_specs(sc)):
+        xs = Hh.T(g["Xs"]).requires_grad_(True)
+        mu, var = O.gp_predict(sp, X, Hh.T(g[f"alpha_{e}"]), Hh.T(g[f"Kinv_{e}"]), xs)
+        gm, = torch.autograd.grad(mu.sum(), xs, retain_graph=True)
+        gv, = torch.autograd.grad(var.sum(), xs)
+        assert relmax(jm[:, e, :], gm.numpy()) < 1e-9
+        assert relmax(jv[:, e, :], gv.numpy()) < 1e-7
+
+
+def _run_rollout(nh, sc, gps, fused_cost=True):
+    plan, ptens = nh.native_plan(sc, gps, need_grad=True, fused_cost=fused_cost)
+    states, inputs = plan.forward(nh.x0_of(sc))
+    return plan, states, inputs
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_rollout_formula(nh, name):
+    """Reference factors in; trajectories, cost and gradients out."""
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    plan, states, inputs = _run_rollout(nh, sc, nh.native_fit(sc, golden=g))
+    close(states, g["states"], 1e-8, 1e-11)
+    close(inputs, g["inputs"], 1e-8, 1e-11)
+    close(plan.cost_out[0], g["cost"], 1e-10)
+    close(plan.cost_out[1], g["std_cost"], 1e-9)
+    gr = plan.backward(grad_cost=1.0)
+    assert relmax(gr["log_ls"], g["g_log_ls"]) < 1e-7
+    assert relmax(gr["centers"], g["g_centers"]) < 1e-7
+    assert relmax(gr["W"], g["g_W"]) < 1e-7
+    if "g_bias" in g:
+        assert relmax(gr["bias"], g["g_bias"]) < 1e-7
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_rollout_end_to_end(nh, name):
+    """Own precompute; north-star tolerances."""
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    plan, states, inputs = _run_rollout(nh, sc, nh.native_fit(sc))
+    close(plan.cost_out[0], g["cost"], REL_VAL)
+    close(plan.cost_out[1], g["std_cost"], 1e-4)
+    assert relmax(states, g["states"]) < REL_VAL
+    gr = plan.backward(grad_cost=1.0)
+    for k in ("log_ls", "centers", "W"):
+        assert relmax(gr[k], g["g_" + k]) < REL_GRAD
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+def test_rollout_generic_cost_path(nh, name):
+    """No fused cost: the caller differentiates its own cost w.r.t. states and hands grad_states back."""
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    plan, states, inputs = _run_rollout(nh, sc, nh.native_fit(sc, golden=g), fused_cost=False)
+    st = states.detach().cpu().requires_grad_(True)
+    cost, _ = O.expected_cost(Hh.oracle_cost(sc, st))
+    cost.backward()
+    gr = plan.backward(grad_states=st.grad.to(states.device))
+    for k in ("log_ls", "centers", "W"):
+        assert relmax(gr[k], g["g_" + k]) < 1e-7
+
+
+def test_backward_finite_differences(nh):
+    """Adjoint kernel in isolation: central differences of the CUDA forward cost (T6 of SURVEY.md §4)."""
+    sc, g = scenarios.scenario("c1"), Hh.load_golden("c1")
+    gps = nh.native_fit(sc, golden=g)
+    plan, ptens = nh.native_plan(sc, gps, need_grad=True)
+    x0 = nh.x0_of(sc)
+    plan.forward(x0)
+    gr = plan.backward(grad_cost=1.0, want_gx0=True)
+    rs = np.random.RandomState(0)
+    for key, gk in (("centers", "centers"), ("W", "W"), ("log_ls", "log_ls")):
+        t = ptens[key]
+        flat = t.view(-1)
+        for i in rs.choice(flat.numel(), size=min(4, flat.numel()), replace=False):
+            h = 1e-6
+            old = float(flat[i])
+            flat[i] = old + h; plan.forward(x0); cp = float(plan.cost_out[0])
+            flat[i] = old - h; plan.forward(x0); cm = float(plan.cost_out[0])
+            flat[i] = old
+            fd = (cp - cm) / (2 * h)
+            an = float(gr[gk].view(-1)[i])
+            assert abs(fd - an) <= 2e-5 * max(abs(an), 1e-3), (key, int(i), fd, an)
+    # gradient w.r.t. the initial particles
+    i, j, h = 3, 1, 1e-6
+    xp = x0.clone(); xp[i, j] += h; plan.forward(xp); cp = float(plan.cost_out[0])
+    xm = x0.clone(); xm[i, j] -= h; plan.forward(xm); cm = float(plan.cost_out[0])
+    an = float(gr["x0"][i, j])
+    assert abs((cp - cm) / (2 * h) - an) <= 2e-5 * max(abs(an), 1e-3)
+
+
+def test_philox_rollout_statistics(nh):
+    """Production noise (counter-based Philox): deterministic per seed, different across seeds, dropout rate and
+    N(0,1) moments as specified; sharding-invariant by construction (keyed by global particle id)."""
+    sc, g = scenarios.scenario("c2"), Hh.load_golden("c2")
+    sc = dict(sc); sc["M"] = 4096
+    gps = nh.native_fit(sc, golden=g)
+    x0 = nh.G(sc["x0_mean"]).repeat(sc["M"], 1)
+    outs = []
+    for seed in (1, 1, 2):
+        plan, _ = nh.native_plan(sc, gps, need_grad=False, inject=False, seed=seed)
+        s, u = plan.forward(x0)
+        outs.append((s.clone(), u.clone(), float(plan.cost_out[0])))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.equal(outs[0][0], outs[2][0])
+    # two half-size shards with particle offsets reproduce the full run bit for bit
+    half = sc["M"] // 2
+    sh = dict(sc); sh["M"] = half
+    parts = []
+    for r in range(2):
+        plan, _ = nh.native_plan(sh, gps, need_grad=False, inject=False, seed=1, particle_offset=r * half)
+        s, _ = plan.forward(x0[r * half:(r + 1) * half])
+        parts.append(s.clone())
+    assert torch.equal(torch.cat(parts, 1), outs[0][0])
+
+
+def test_size_independent_properties_large(nh):
+    """Sweep-sized GP (N = 2048): identities that hold for any size, checked on the CUDA results alone.
+    At a training input x_i:  mean = y_i - sn2 * alpha_i  and  var = sn2 * (1 - sn2 * Kinv_ii)."""
+    from mcpilco_b200 import _ops as ops
+    from mcpilco_b200 import _pack as P
+    gen = torch.Generator().manual_seed(0)
+    Nn = 2048
+    X, Y = O.cartpole_dataset(Nn, 0.1, gen)
+    spec = P.spec_from_dict({"D": 6, "log_ls": [2, 2, 2, 0.8, 1.5, 2.5], "lambda": 1.0, "mean": 0.0,
+                             "mpk": [np.exp([-5, -5, -5, -4, -4, -4, -3.0]), np.exp([-5, -5, -4, -2, -1, -4.0] * 2)], "sigma_n": 0.1})
+    Xg, yg = X.to("cuda:0"), Y[:, 0:1].contiguous().to("cuda:0")
+    alpha, Kinv = ops.gp_precompute(spec, Xg, yg)
+    K = ops.gp_covariance(spec, Xg, None, add_noise=True)
+    resid = (K @ alpha - yg).abs().max().item()
+    assert resid < 1e-9, resid
+    I = torch.eye(Nn, dtype=torch.float64, device="cuda:0")
+    assert (Kinv @ K - I).abs().max().item() < 1e-8
+    gp = ops.FittedGp(spec, Xg, alpha, Kinv)
+    mean, var = ops.gp_predict([gp], Xg[:512])
+    sn2 = 0.01
+    close(mean[:, 0], (yg[:512, 0] - sn2 * alpha[:512, 0]).cpu().numpy(), 1e-7, 1e-9)
+    close(var[:, 0], (sn2 * (1 - sn2 * torch.diagonal(Kinv)[:512])).cpu().numpy(), 1e-5, 1e-10)
+    # and against the oracle formula on a handful of fresh points (CPU finishes in seconds at this size)
+    Xs = X[:16] + 0.05
+    sp_o = O.make_spec(6, log_ls=[2, 2, 2, 0.8, 1.5, 2.5], mpk_log_pars=[[-5, -5, -5, -4, -4, -4, -3.0], [-5, -5, -4, -2, -1, -4.0] * 2],
+                       sigma_n=0.1)
+    mo, vo = O.gp_predict(sp_o, X, alpha.cpu(), Kinv.cpu().contiguous(), Xs)
+    mg, vg = ops.gp_predict([gp], Xs.to("cuda:0"))
+    close(mg, mo.numpy(), 1e-9, 1e-12)
+    close(vg[:, 0], vo.numpy(), REL_VAL)
+
+
+def test_edge_cases(nh):
+    from mcpilco_b200 import _native as Nn
+    from mcpilco_b200 import _ops as ops
+    sc, g = scenarios.scenario("c2"), Hh.load_golden("c2")
+    gps = nh.native_fit(sc, golden=g)
+    # empty test set
+    mean, var = ops.gp_predict(gps, torch.empty(0, sc["D"], dtype=torch.float64, device="cuda:0"))
+    assert mean.shape == (0, 2) and var.shape == (0, 2)
+    # single particle, horizon 1 (only the initial policy evaluation)
+    s1 = dict(sc); s1["M"], s1["H"] = 1, 1
+    s1["eps"], s1["masks"] = sc["eps"][:0, :1], sc["masks"][:1, :1]
+    plan, _ = nh.native_plan(s1, gps, need_grad=False)
+    st, inp = plan.forward(nh.x0_of(sc)[:1])
+    close(st[0], g["states"][0, :1], 1e-12)
+    close(inp[0], g["inputs"][0, :1], 1e-9)
+    # N = 1 training point, odd N
+    X1 = nh.G(sc["X"][:1]); y1 = nh.G(sc["Y"][:1, :1])
+    sp = nh.native_specs(sc)[0]
+    a1, K1 = ops.gp_precompute(sp, X1, y1)
+    k = 1.0 + np.exp(-4.2) ** 2
+    close(K1, [[1.0 / k]], 1e-13); close(a1, sc["Y"][:1, :1] / k, 1e-13)
+    X5 = nh.G(sc["X"][:5]); y5 = nh.G(sc["Y"][:5, :1])
+    a5, K5 = ops.gp_precompute(sp, X5, y5)
+    Kn = ops.gp_covariance(sp, X5, None, add_noise=True)
+    close(K5 @ Kn, np.eye(5), 0, 1e-10)
+    # errors are loud: CPU tensors are rejected, bad shapes return MCP_E_ARG
+    with pytest.raises(RuntimeError):
+        ops.gp_covariance(sp, torch.zeros(3, 6, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        ops.gp_predict(gps, torch.zeros(3, 5, dtype=torch.float64, device="cuda:0"))
+    # non-SPD input propagates NaN instead of raising (MC_PILCO.py:451,497 rely on it)
+    bad = P_bad_spec(nh)
+    a, K = ops.gp_precompute(bad, X5, y5)
+    assert torch.isnan(a).any() or torch.isinf(a).any() or (a.abs() > 1e6).any()
+
+
+def P_bad_spec(nh):
+    from mcpilco_b200 import _pack as P
+    s = P.spec_from_dict({"D": 6, "log_ls": [50.0] * 6, "lambda": 1.0, "mean": 0.0, "mpk": [], "sigma_n": 0.0})
+    return s  # lengthscales so long that K is numerically rank one and sigma_n = 0: Cholesky breaks down
