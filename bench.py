@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of one GP particle rollout, forward + backward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path (mcpilco_b200)
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference algorithm on the host CPU (oracle port)
+
+A "step" is what one iteration of MC_PILCO.reinforce_policy does on the hot path (reference MC_PILCO.py:484-522):
+apply_policy -> cost_function -> cost.backward(), i.e. M*H particle-steps forward and backward, including the cost, the
+gradient reduction and (N > 1) the collectives.  Workload (config.workload): the "synthetic cartpole GP scaling sweep" point
+N = 8192 training points, horizon 60, SE + polynomial kernel, E = 2 outputs, nb = 200 policy with dropout 0.25, M particles
+PER GPU (weak scaling; 8 GPUs x 131072 is the north-star M = 1M — pass --particles-per-gpu 131072 for that; throughput per
+particle-step does not depend on M beyond ~4k).  Precompute (Cholesky etc.) is outside the metric and reported
+in config.precompute_ms.  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mc-pilco_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FP64_PEAK_TFLOPS = 37.15  # measured on this pool's B200: DMMA.8x8x4 issue-bound, 3 s sustained (profiles/microbench/r01_fp64_peaks.txt)
+METRIC = "particle-steps/s (rollout fwd+bwd)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--train-points", type=int, default=8192)
+    ap.add_argument("--particles-per-gpu", type=int, default=8192)
+    ap.add_argument("--horizon", type=int, default=60)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-particles", type=int, default=512)
+    ap.add_argument("--cpu-horizon", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--se-only", action="store_true", help="config 2 kernel (pure squared-exponential)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference algorithm on the host cores (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_rollout_sample(sc, M, H, threads, repeats, warmup, fitted=None):
+    """Times `repeats` fwd+bwd rollouts of M particles x H steps with the oracle (torch CPU fp64, autograd) on the workload `sc`.
+    `fitted`: optional [(alpha, Kinv)] per output (CPU tensors) to skip the O(N^3) fit, which is outside the metric."""
+    from oracle import mcpilco_oracle as O
+    torch.set_num_threads(threads)
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+    X = T(sc["X"])
+    gps = []
+    for e, g in enumerate(sc["gps"]):
+        sp = O.make_spec(sc["D"], log_ls=g["log_ls"], log_lambda=float(np.log(g["lambda"])), mean=g["mean"],
+                         mpk_log_pars=[np.log(w) for w in g["mpk"]], sigma_n=g["sigma_n"])
+        if fitted is None:
+            alpha, _, Kinv = O.gp_fit(sp, X, T(sc["Y"][:, e:e + 1]))
+        else:
+            alpha, Kinv = fitted[e]
+        gps.append((sp, X, alpha, Kinv))
+    m = dict(sc["model"]); m.update(Ds=sc["Ds"], Du=sc["Du"], norm=[1.0] * sc["E"])
+    p = sc["policy"]
+    rs = np.random.RandomState(1)
+    times = []
+    for it in range(warmup + repeats):
+        pol = {"kind": p["kind"], "log_ls": T(np.log(p["lengthscales"])).reshape(1, -1).requires_grad_(True),
+               "centers": T(p["centers"]).requires_grad_(True), "W": T(p["weight"]).requires_grad_(True), "bias": None,
+               "u_max": p["u_max"], "scale": torch.ones(1, p["centers"].shape[1], dtype=torch.float64),
+               "angle": list(p["angle"]), "non_angle": list(p["non_angle"])}
+        eps0, eps = T(rs.randn(M, sc["Ds"])), T(rs.randn(H - 1, M, sc["E"]))
+        masks = T((rs.rand(H, M, p["nb"]) >= sc["p_dropout"]).astype(np.float64))
+        t0 = time.perf_counter()
+        x0 = O.initial_particles(T(sc["x0_mean"]), T(sc["x0_var"]), eps0)
+        st, inp = O.rollout(m, gps, pol, x0, eps, masks, sc["p_dropout"])
+        c = sc["cost"]
+        cost, std = O.expected_cost(O.cost_cart_pole(st, T(c["target"]), T(c["ls"]), c["angle_index"], c["pos_index"]))
+        cost.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # the CPU baseline is one process on rank 0
+    from mcpilco_b200 import workloads as W
+    sc = W.cartpole_sweep(args.train_points, se_only=args.se_only)
+    cores = host_cores()
+    M, H = args.cpu_particles, args.cpu_horizon
+    times = cpu_rollout_sample(sc, M, H, cores, args.steps, args.warmup)
+    ms = 1e3 * float(np.sum(times))
+    value = M * H * len(times) / float(np.sum(times))
+    sample = "oracle port (torch CPU fp64 + autograd) of the same workload at M=%d particles x H=%d steps per step (memory ~ M*N*H*E forbids the full size), %d threads" % (M, H, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / max(len(times), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "c5 synthetic cartpole GP sweep point: N=%d training points, M=%d particles/GPU (global %d), horizon %d, E=2, D=6, %s kernel, "
+                        "nb=200 policy, p_dropout=0.25, Cart_pole_cost, Philox noise" % (args.train_points, args.particles_per_gpu,
+                                                                                        args.particles_per_gpu * world, args.horizon,
+                                                                                        "SE" if args.se_only else "SE+MPK(2)"),
+            "train_points": args.train_points, "particles_per_gpu": args.particles_per_gpu, "horizon": args.horizon,
+            "parallelism": "particle-dp%d" % world, "l2": "inputs larger than L2 (Kinv 2 x %d MB, K*/V chunks >= 1 GB)" % (args.train_points ** 2 * 8 >> 20)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi samples of one GPU while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+def build_objects(sc, dev):
+    """The reference's construction sequence (test_mcpilco_cartpole.py:49-231) against mcpilco_b200's classes."""
+    import mcpilco_b200.model_learning.Model_learning as ML
+    import mcpilco_b200.policy_learning.Cost_function as CF
+    import mcpilco_b200.policy_learning.MC_PILCO as MCP
+    import mcpilco_b200.policy_learning.Policy as PO
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device=dev)  # noqa: E731
+    D = sc["D"]
+    dicts = []
+    for g in sc["gps"]:
+        rbf = dict(active_dims=np.arange(D), lengthscales_init=np.exp(g["log_ls"]), lambda_init=np.array([g["lambda"]]), flg_train_lambda=False,
+                   sigma_n_init=np.array([g["sigma_n"]]), dtype=torch.float64, device=dev)
+        mpk = dict(active_dims=np.arange(D), poly_deg=len(g["mpk"]), Sigma_pos_par_init_list=list(g["mpk"]),
+                   flg_train_Sigma_pos_par_list=[True] * len(g["mpk"]), dtype=torch.float64, device=dev)
+        dicts.append([rbf, mpk] if g["mpk"] else rbf)
+    m, p, c = sc["model"], sc["policy"], sc["cost"]
+    cls = ML.Speed_Model_learning_RBF_MPK_angle_state if sc["gps"][0]["mpk"] else ML.Speed_Model_learning_RBF_angle_state
+    model_par = dict(num_gp=sc["E"], init_dict_list=dicts, T_sampling=m["T"], angle_indeces=m["angle"], not_angle_indeces=m["not_angle"],
+                     vel_indeces=m["vel"], not_vel_indeces=m["pos"], device=dev)
+    policy_par = dict(state_dim=sc["Ds"], input_dim=sc["Du"], num_basis=p["nb"], angle_indices=p["angle"], non_angle_indices=p["non_angle"],
+                      lengthscales_init=p["lengthscales"], centers_init=p["centers"], weight_init=p["weight"], flg_squash=True,
+                      u_max=p["u_max"], flg_drop=True, device=dev)
+    cost_par = dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), angle_index=c["angle_index"], pos_index=c["pos_index"])
+    obj = MCP.MC_PILCO(T_sampling=m["T"], state_dim=sc["Ds"], input_dim=sc["Du"], f_sim=None, f_model_learning=cls, model_learning_par=model_par,
+                       f_rand_exploration_policy=None, rand_exploration_policy_par=None, f_control_policy=PO.Sum_of_gaussians_with_angles,
+                       control_policy_par=policy_par, f_cost_function=CF.Cart_pole_cost, cost_function_par=cost_par, device=dev)
+    ml = obj.model_learning
+    ml.gp_inputs = T(sc["X"])
+    ml.gp_output_list = [T(sc["Y"][:, e:e + 1]) for e in range(sc["E"])]
+    ml.dim_state, ml.dim_input, ml.num_samples = sc["Ds"], sc["Du"], sc["N"]
+    return obj
+
+
+def own_arm(args):
+    import torch.distributed as dist
+    from mcpilco_b200 import _ops as ops
+    from mcpilco_b200 import workloads as W
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device — the hot path has no CPU fallback")
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sc = W.cartpole_sweep(args.train_points, se_only=args.se_only)
+    obj = build_objects(sc, dev)
+    ml, pol = obj.model_learning, obj.control_policy
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    import contextlib
+    with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
+        for e in range(sc["E"]):
+            ml.pretrain_gp(e)
+    torch.cuda.synchronize()
+    precompute_ms = 1e3 * (time.perf_counter() - t0)
+    ml.set_eval_mode()
+    M_global, H = args.particles_per_gpu * world, args.horizon
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device=dev)  # noqa: E731
+    mean_d, var_d = T(sc["x0_mean"]), T(sc["x0_var"])
+    kw = dict(flg_particles_init_uniform=False, particles_init_up_bound=None, particles_init_low_bound=None,
+              flg_particles_init_multi_gauss=False, num_particles=M_global, T_control=H, p_dropout=sc["p_dropout"])
+    params = [pol.log_lengthscales, pol.centers, pol.f_linear.weight]
+
+    def step(mean=mean_d, var=var_d):
+        for p in params:
+            p.grad = None
+        states, inputs = obj.apply_policy(particles_initial_state_mean=mean, particles_initial_state_var=var, **kw)
+        cost, std = obj.cost_function(states, inputs, 0)
+        cost.backward()
+        return cost, std
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    torch.manual_seed(0)
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: inputs resident in HBM ----
+    barrier()
+    ops.prof_enable(True)
+    ops.launch_count(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        cost, std = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler is not None else None
+    launches = ops.launch_count(reset=True)
+    gemm_ms, gemm_n, gemm_fl = ops.prof_read()
+    ops.prof_enable(False)
+    cost_v = float(cost.detach())
+    value = M_global * H * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, host results out, through the same public API ----
+    host_in = [p.detach().cpu().pin_memory() for p in params] + [mean_d.cpu().pin_memory(), var_d.cpu().pin_memory()]
+    host_out = [torch.empty(n, dtype=torch.float64).pin_memory() for n in (2, pol.log_lengthscales.numel(), pol.centers.numel(), pol.f_linear.weight.numel())]
+    h2d = sum(t.numel() * 8 for t in host_in)
+    d2h = sum(t.numel() * 8 for t in host_out)
+
+    def e2e_step():
+        with torch.no_grad():
+            for p, h in zip(params, host_in[:3]):
+                p.copy_(h, non_blocking=True)
+        mean = host_in[3].to(dev, non_blocking=True)
+        var = host_in[4].to(dev, non_blocking=True)
+        c, s = step(mean, var)
+        host_out[0].copy_(torch.stack([c.detach(), s.detach()]), non_blocking=True)
+        for h, p in zip(host_out[1:], params):
+            h.copy_(p.grad.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the host reads the result
+
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = M_global * H * args.e2e_steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    Ns = [g.N for g in ml.fitted_gps()]
+    F = W.flops_per_particle_step(Ns, sc["D"], need_grad=True)
+    achieved = gemm_fl / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None
+    traffic = None
+    prof_json = os.path.join(ROOT, "profiles", "ncu_gemm_summary.json")
+    if os.path.exists(prof_json):
+        try:
+            traffic = json.load(open(prof_json)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args, world), precompute_ms=precompute_ms, cost=cost_v, e2e_steps=args.e2e_steps,
+                           flops_per_particle_step=F, step_tflops_per_gpu=F * value / world * 1e-12,
+                           step_frac_of_fp64_peak=F * value / world * 1e-12 / FP64_PEAK_TFLOPS),
+            "roofline": {"bound": "tensor", "kernel": "dgemm_nt_kernel (V = K* Kinv, FP64 DMMA.8x8x4)", "achieved": achieved,
+                         "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": None if achieved is None else achieved / FP64_PEAK_TFLOPS,
+                         "traffic": traffic, "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                         "flops_per_launch": gemm_fl / max(gemm_n, 1), "kernel_share_of_step": gemm_ms / ms,
+                         "peak_source": "own measurement on this pool (FP64 is absent from MEASURED_PEAKS.json): profiles/microbench/r01_fp64_peaks.txt"},
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.e2e_steps},
+            "gpu_launches": launches, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        fitted = [(g.alpha.detach().cpu().reshape(-1, 1), g.Kinv.detach().cpu().contiguous()) for g in ml.fitted_gps()]
+        Mc, Hc = args.cpu_particles, args.cpu_horizon
+        times = cpu_rollout_sample(sc, Mc, Hc, cores, repeats=2, warmup=1, fitted=fitted)
+        line["cpu_baseline"] = {"value": Mc * Hc * len(times) / float(np.sum(times)), "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                                "sample": "oracle port (torch CPU fp64 + autograd) of the same workload at M=%d x H=%d per rollout, 2 timed "
+                                          "rollouts after 1 warm-up, %d threads" % (Mc, Hc, cores)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(reference_arm(a) if a.impl == "reference" else own_arm(a))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 1
+#define MCP_ABI_VERSION 2
 
 #define MCP_MAX_D 32    /* gp-input dimension            */
 #define MCP_MAX_DS 16   /* state dimension               */
@@ -214,6 +214,25 @@ int mcpilco_gp_predict(const McpGp* gps, int E, const double* Xs, int M, double*
 size_t mcpilco_rollout_workspace_bytes(int M, int H, int E, int D, int Nmax, int nb, int Dp, int Du);
 int mcpilco_rollout_fwd(const McpRollout* r, void* stream);
 int mcpilco_rollout_bwd(const McpRollout* r, const McpRolloutGrad* g, void* stream);
+
+/* u[M, Du] = pi(x[M, Ds]) at time index t: sum of Gaussians, dropout (injected masks for step t or Philox), linear layer,
+ * tanh squashing.  Replaces Sum_of_gaussians.forward and its two wrappers (policy_learning/Policy.py:242-265,323-335,
+ * 389-403).  `masks_t` is [M, nb] or NULL. */
+int mcpilco_policy_forward(const McpPolicy* policy, int M, int t, const double* x, double p_dropout, const uint8_t* masks_t,
+                           uint64_t seed, uint64_t particle_offset, double* u, void* stream);
+
+/* Initial particles (MC_PILCO.apply_policy, policy_learning/MC_PILCO.py:635-657) from counter-based Philox keyed by the
+ * global particle id:  kind 0: x0 = a[k] + b[k] * n, n ~ N(0, I)  (a = mean, b = sqrt(var); n_modes > 1 draws the mode k
+ * uniformly per particle: the multi-modal Gaussian of :640-647);  kind 1: x0 = a + (b - a) * u, u ~ U(0,1) (a = low, b = up
+ * bound, :635-639).  a, b are DEVICE arrays [n_modes, Ds]. */
+int mcpilco_init_particles(int kind, const double* a, const double* b, int n_modes, int M, int Ds, uint64_t seed,
+                           uint64_t particle_offset, double* x0, void* stream);
+
+/* Timing hook for bench.py's roofline: when enabled, every launch of the dominant kernel (the FP64 tensor-core GEMM
+ * V = K* Kinv of the posterior) is bracketed by CUDA events on the launching stream.  read() synchronises those events and
+ * returns the summed kernel time (ms), the number of bracketed launches and their summed flop count (2 m n k each). */
+int mcpilco_prof_enable(int on);
+int mcpilco_prof_read(double* total_ms, uint64_t* launches, double* flops);
 
 /* sizeof() of {McpGpSpec, McpGp, McpModel, McpPolicy, McpCost, McpMeas, McpNoise, McpRollout, McpRolloutGrad};
  * returns how many there are.  Lets a binding check its struct layout. */

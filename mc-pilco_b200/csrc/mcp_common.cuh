@@ -11,6 +11,9 @@ namespace mcp {
 // ---- host-side error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// bench.py's roofline hook: bracket a launch of the dominant kernel with events (no-ops unless enabled)
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st, double flops);
 
 #define MCP_CHECK_ARG(cond, ...)          \
   do {                                    \
@@ -99,7 +102,7 @@ __device__ __forceinline__ void box_muller(const Philox4& p, double& n0, double&
   n1 = r * s;
 }
 // streams of the rollout: which random object a counter addresses
-enum { RNG_EPS = 0, RNG_MASK = 1, RNG_MEAS = 2 };
+enum { RNG_EPS = 0, RNG_MASK = 1, RNG_MEAS = 2, RNG_X0 = 3 };
 // standard normal #j of (particle, t, stream)
 __device__ __forceinline__ double rng_normal(uint64_t seed, uint64_t pid, int t, int stream, int j) {
   Philox4 p = philox4x32_10(seed, (uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)t | ((uint32_t)stream << 24), (uint32_t)(j >> 1));

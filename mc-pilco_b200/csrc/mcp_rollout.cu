@@ -30,8 +30,9 @@ __device__ __forceinline__ double policy_feature(const McpPolicy& p, const doubl
 
 __device__ __forceinline__ bool dropout_active(const McpPolicy& p, const McpNoise& nz) { return p.use_drop && nz.p_dropout > 0.0; }
 
-__device__ __forceinline__ bool keep_unit(const McpNoise& nz, int M, int nb, int t, int m, int b) {
-  if (nz.masks) return nz.masks[((size_t)t * M + m) * nb + b] != 0;
+// tm addresses the injected mask tensor, t the Philox counter (they differ only for the stand-alone policy call)
+__device__ __forceinline__ bool keep_unit(const McpNoise& nz, int M, int nb, int tm, int t, int m, int b) {
+  if (nz.masks) return nz.masks[((size_t)tm * M + m) * nb + b] != 0;
   return rng_keep(nz.seed, nz.particle_offset + (uint64_t)m, t, b, nz.p_dropout);
 }
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ void cost_grad_add(const McpCost& c, const double* __
 // u_t = pi(pol_in_t) with dropout and squashing, one warp per particle; then the gp-input features
 // of (x_t, u_t).  Policy.py:242-265; Model_learning.py:670-683.
 __global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
-                                                         const __grid_constant__ McpNoise nz, int M, int t,
+                                                         const __grid_constant__ McpNoise nz, int M, int t, int tm,
                                                          const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
                                                          double* __restrict__ u_t, double* __restrict__ Xs) {
   __shared__ double s_il[MCP_MAX_DP];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__
       d = fma(r, r, d);
     }
     double h = exp(-d);
-    if (drop) h = keep_unit(nz, M, pol.nb, t, m, b) ? h * keep_scale : 0.0;
+    if (drop) h = keep_unit(nz, M, pol.nb, tm, t, m, b) ? h * keep_scale : 0.0;
 #pragma unroll
     for (int k = 0; k < MCP_MAX_DU; k++)
       if (k < pol.Du) a[k] = fma(pol.W[(size_t)k * pol.nb + b], h, a[k]);
@@ -193,6 +194,28 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
       nv[(size_t)m * ms.n_pos + i] = nv_new;
       pn[ip] = np_new;
       pn[iv] = mv_new;
+    }
+  }
+}
+
+// initial particles from Philox (MC_PILCO.py:635-657); stream RNG_X0, "time" index 0
+__global__ void init_particles_kernel(int kind, const double* __restrict__ a, const double* __restrict__ b, int n_modes, int M, int Ds,
+                                      uint64_t seed, uint64_t offset, double* __restrict__ x0) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  uint64_t pid = offset + (uint64_t)m;
+  int k = 0;
+  if (n_modes > 1) {
+    Philox4 q = philox4x32_10(seed, (uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)RNG_X0 << 24, 0xFFFFFFFFu);
+    k = (int)(((uint64_t)q.v[0] * (uint64_t)n_modes) >> 32);
+  }
+  for (int j = 0; j < Ds; j++) {
+    double lo = a[(size_t)k * Ds + j], hi = b[(size_t)k * Ds + j];
+    if (kind == 0) {
+      x0[(size_t)m * Ds + j] = fma(hi, rng_normal(seed, pid, 0, RNG_X0, j), lo);
+    } else {
+      Philox4 q = philox4x32_10(seed, (uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)RNG_X0 << 24, (uint32_t)j);
+      x0[(size_t)m * Ds + j] = fma(hi - lo, u01(q.v[0], q.v[1]), lo);
     }
   }
 }
@@ -357,7 +380,7 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
           for (int j = 0; j < DPT; j++)
             if (j < Dp) { double q = (s_z[j] - cb[j]) * s_il[j]; d = fma(q, q, d); }
           double h = exp(-d);
-          if (drop) h = keep_unit(r.noise, M, nb, t, m, b) ? h * keep_scale : 0.0;
+          if (drop) h = keep_unit(r.noise, M, nb, t, t, m, b) ? h * keep_scale : 0.0;
           double lh = 0.0;
 #pragma unroll
           for (int k = 0; k < DUT; k++)
@@ -584,7 +607,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   for (int t = 0; t < H; t++) {
     const double* x_t = r->states + (size_t)t * M * Ds;
     const double* p_t = meas ? r->pol_in + (size_t)t * M * Ds : x_t;
-    policy_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(r->policy, r->model, r->noise, M, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
+    policy_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(r->policy, r->model, r->noise, M, t, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
                                                   t < H - 1 ? w.Xs : nullptr);
     MCP_LAUNCH_CHECK();
     if (t == H - 1) break;
@@ -633,6 +656,41 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_bwd(const 
   reduce_partials_kernel<<<cdiv(nparam, 128), 128, 0, st>>>(w.partials, w.bwd_ctas, nparam, w.flat);
   MCP_LAUNCH_CHECK();
   scatter_grads_kernel<<<cdiv(nparam, 128), 128, 0, st>>>(w.flat, Dp, nb, Du, g->g_log_ls, g->g_centers, g->g_W, g->g_bias);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_policy_forward(const McpPolicy* policy, int M, int t, const double* x, double p_dropout,
+                                                                              const uint8_t* masks_t, uint64_t seed, uint64_t particle_offset,
+                                                                              double* u, void* stream) {
+  MCP_CHECK_ARG(policy != nullptr && M >= 0, "policy_forward: null policy");
+  const McpPolicy& p = *policy;
+  MCP_CHECK_ARG(p.nb >= 1 && p.nb <= 512 && p.Dp >= 1 && p.Dp <= MCP_MAX_DP && p.Du >= 1 && p.Du <= MCP_MAX_DU && p.Ds >= 1 && p.Ds <= MCP_MAX_DS,
+                "policy_forward: policy dims out of range (nb=%d Dp=%d Du=%d Ds=%d)", p.nb, p.Dp, p.Du, p.Ds);
+  int dp = p.kind == 1 ? p.n_na + 2 * p.n_a : (p.kind == 2 ? 2 * p.Ds : p.Ds);
+  MCP_CHECK_ARG(dp == p.Dp, "policy_forward: feature dimension %d does not match kind %d (%d)", p.Dp, p.kind, dp);
+  MCP_CHECK_ARG(p.log_ls && p.centers && p.W && (!p.has_bias || p.bias) && (p.kind != 2 || p.target_traj), "policy_forward: null policy tensor");
+  MCP_CHECK_ARG(p_dropout >= 0.0 && p_dropout < 1.0, "policy_forward: p_dropout outside [0,1)");
+  if (M == 0) return MCP_OK;
+  MCP_CHECK_ARG(x && u, "policy_forward: null state / input buffer");
+  McpModel mdl{};
+  McpNoise nz{};
+  nz.masks = masks_t;
+  nz.seed = seed;
+  nz.particle_offset = particle_offset;
+  nz.p_dropout = p_dropout;
+  policy_fwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(p, mdl, nz, M, t, 0, x, x, u, nullptr);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_init_particles(int kind, const double* a, const double* b, int n_modes, int M, int Ds,
+                                                                              uint64_t seed, uint64_t particle_offset, double* x0, void* stream) {
+  MCP_CHECK_ARG((kind == 0 || kind == 1) && a && b && n_modes >= 1 && M >= 0 && Ds >= 1 && Ds <= MCP_MAX_DS && (kind == 0 || n_modes == 1),
+                "init_particles: bad arguments (kind=%d n_modes=%d M=%d Ds=%d)", kind, n_modes, M, Ds);
+  if (M == 0) return MCP_OK;
+  MCP_CHECK_ARG(x0 != nullptr, "init_particles: null output");
+  init_particles_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(kind, a, b, n_modes, M, Ds, seed, particle_offset, x0);
   MCP_LAUNCH_CHECK();
   return MCP_OK;
 }

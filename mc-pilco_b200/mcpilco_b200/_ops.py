@@ -273,3 +273,50 @@ class RolloutPlan:
 
 def launch_count(reset=False):
     return int(N.lib().mcpilco_launch_count(1 if reset else 0))
+
+
+def policy_forward(pst, tens, x, t=0, p_dropout=0.0, masks_t=None, seed=0, particle_offset=0):
+    """u = pi(x) for a batch of states through the CUDA policy kernel.  Policy.py:242-265,323-335,389-403."""
+    x = _c(x, "states")
+    L = _enter(x.device)
+    if x.dim() != 2 or x.shape[1] != pst.Ds:
+        raise RuntimeError("policy_forward: states must be [M, %d]" % pst.Ds)
+    M = x.shape[0]
+    u = torch.empty(M, pst.Du, dtype=F64, device=x.device)
+    keep = [_c(tens[k], k) for k in ("log_ls", "centers", "W")]
+    pst.log_ls, pst.centers, pst.W = (k.data_ptr() for k in keep)
+    b = _c(tens["bias"], "bias") if tens.get("bias") is not None else None
+    tr = _c(tens["target_traj"], "target_traj") if tens.get("target_traj") is not None else None
+    if tr is not None and not (0 <= int(t) < tr.shape[0]):
+        raise RuntimeError("policy_forward: time index %s outside the target trajectory" % t)
+    pst.bias = b.data_ptr() if b is not None else None
+    pst.target_traj = tr.data_ptr() if tr is not None else None
+    mk = None
+    if masks_t is not None:
+        mk = masks_t.detach().to(torch.uint8).contiguous()
+        if not mk.is_cuda or tuple(mk.shape) != (M, pst.nb):
+            raise RuntimeError("policy_forward: masks must be a CUDA tensor [M, nb]")
+    N.check(L.mcpilco_policy_forward(C.byref(pst), M, int(t or 0), _ptr(x), float(p_dropout), _ptr(mk), int(seed), int(particle_offset),
+                                     _ptr(u), _stream(x.device)))
+    return u
+
+
+def init_particles(kind, a, b, M, seed=0, particle_offset=0):
+    """Initial particles keyed by the global particle id.  kind "gauss": a = mean(s) [n_modes, Ds], b = std(s);
+    kind "uniform": a = lower, b = upper bound.  MC_PILCO.py:635-657."""
+    a, b = _c(a, "a").reshape(-1, a.shape[-1]), _c(b, "b").reshape(-1, b.shape[-1])
+    L = _enter(a.device)
+    x0 = torch.empty(int(M), a.shape[1], dtype=F64, device=a.device)
+    N.check(L.mcpilco_init_particles(0 if kind == "gauss" else 1, _ptr(a), _ptr(b), a.shape[0], int(M), a.shape[1], int(seed),
+                                     int(particle_offset), _ptr(x0), _stream(a.device)))
+    return x0
+
+
+def prof_enable(on=True):
+    N.check(N.lib().mcpilco_prof_enable(1 if on else 0))
+
+
+def prof_read():
+    ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
+    N.check(N.lib().mcpilco_prof_read(C.byref(ms), C.byref(n), C.byref(fl)))
+    return ms.value, int(n.value), fl.value

@@ -1,0 +1,200 @@
+"""GP prior base classes — the reference's `gpr_lib/GP_prior/GP_prior.py` surface for the rollout hot path.
+
+Same class names, constructor arguments, parameter names (`sigma_n_log`) and method signatures as the reference
+(GP_prior :22-257, Combine_GP :260-296, Sum_Independent_GP :299-347), so reference `state_dict`s load unchanged
+and callers need no edits.  What differs is where the arithmetic runs: a kernel tree is flattened once into a
+POD `McpGpSpec` (`_fill_spec`) and every covariance / factorisation / posterior is one call into
+libmcpilco_b200.so (CUDA, float64).  CPU tensors are rejected: there is no fallback.
+
+Out of scope here: `fit_model` (hyper-parameter training), `Multiply_GP_prior`, `Scale_GP_prior`.
+"""
+import numpy as np
+import torch
+
+from ... import _ops as ops
+from ... import _pack as P
+
+
+class GP_prior(torch.nn.Module):
+    """Superclass of the GP models (reference GP_prior.py:22-257)."""
+
+    def __init__(self, active_dims, sigma_n_init=None, flg_train_sigma_n=True, name="", dtype=torch.float64, sigma_n_num=None,
+                 device=None):
+        super().__init__()
+        self.name = name
+        self.dtype = dtype
+        self.device = torch.device("cpu") if device is None else device
+        self.active_dims = None if active_dims is None else torch.tensor(active_dims, requires_grad=False, device=device, dtype=torch.long)
+        self.GP_with_noise = sigma_n_init is not None
+        if self.GP_with_noise:
+            self.sigma_n_log = torch.nn.Parameter(torch.tensor(np.log(sigma_n_init), dtype=self.dtype, device=self.device),
+                                                  requires_grad=flg_train_sigma_n)
+        self.sigma_n_num = torch.as_tensor(0.0 if sigma_n_num is None else sigma_n_num, dtype=self.dtype, device=self.device)
+        self._spec_cache = {}
+
+    # ---- bookkeeping identical in behaviour to the reference -------------------------------------------------
+    def to(self, dev):
+        super().to(dev)
+        self.device = dev
+        self.sigma_n_num = self.sigma_n_num.to(dev)
+        if self.active_dims is not None:
+            self.active_dims = self.active_dims.to(dev)
+
+    def set_eval_mode(self):
+        self.flg_trainable_list = []
+        for p in self.parameters():
+            self.flg_trainable_list.append(p.requires_grad)
+            p.requires_grad = False
+
+    def set_training_mode(self):
+        for i, p in enumerate(self.parameters()):
+            p.requires_grad = self.flg_trainable_list[i]
+
+    def get_sigma_n_2(self):
+        return torch.exp(self.sigma_n_log) ** 2 + self.sigma_n_num ** 2
+
+    def print_model(self):
+        print(self.name + " parameters:")
+        for par_name, par_value in self.named_parameters():
+            print("-", par_name, ":", par_value.data)
+
+    # ---- flattening ----------------------------------------------------------------------------------------
+    def _fill_spec(self, spec):
+        """Add this kernel's term(s) to `spec` and return the constant prior mean it contributes."""
+        raise NotImplementedError()
+
+    def _noise_value(self):
+        return float(P._np(self.get_sigma_n_2()).reshape(-1)[0]) if self.GP_with_noise else 0.0
+
+    def gp_spec(self, D):
+        """McpGpSpec of this kernel for a D-dimensional gp input; rebuilt only when a parameter changed."""
+        key = (int(D),) + tuple((id(p), p._version) for p in self.parameters())
+        hit = self._spec_cache.get("k")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        spec = P.new_gp_spec(int(D))
+        with torch.no_grad():
+            spec.mean0 = float(self._fill_spec(spec))
+            spec.sigma_n2 = self._noise_value()
+        self._spec_cache["k"] = (key, spec)
+        return spec
+
+    # ---- arithmetic: all native ------------------------------------------------------------------------------
+    def get_mean(self, X):
+        """Constant prior mean in X, [N, 1]."""
+        return torch.full((X.shape[0], 1), self.gp_spec(X.shape[1]).mean0, dtype=self.dtype, device=X.device)
+
+    def get_covariance(self, X1, X2=None, flg_noise=False):
+        """k(X1, X2); the noise variance is added on the diagonal only for X2=None, flg_noise and a noisy GP."""
+        return ops.gp_covariance(self.gp_spec(X1.shape[1]), X1, X2, add_noise=bool(flg_noise) and self.GP_with_noise and X2 is None)
+
+    def get_diag_covariance(self, X, flg_noise=False):
+        d = ops.gp_diag_covariance(self.gp_spec(X.shape[1]), X)
+        if flg_noise and self.GP_with_noise:
+            d = d + self.gp_spec(X.shape[1]).sigma_n2
+        return d
+
+    def forward(self, X):
+        """(m_X, K_X, K_X^-1, log det K_X) through the blocked Cholesky of the precompute (reference :91-115)."""
+        spec = self.gp_spec(X.shape[1])
+        K_X = ops.gp_covariance(spec, X, None, add_noise=self.GP_with_noise)
+        zero = torch.zeros(X.shape[0], 1, dtype=self.dtype, device=X.device)
+        _, K_X_inv, L = ops.gp_precompute(spec, X, zero, want_L=True)
+        log_det = 2 * torch.sum(torch.log(torch.diagonal(L)))
+        return self.get_mean(X), K_X, K_X_inv, log_det
+
+    def get_alpha(self, X, Y):
+        """alpha = K_X^-1 (Y - m_X)  (reference :130-135)."""
+        alpha, K_X_inv = ops.gp_precompute(self.gp_spec(X.shape[1]), X, Y)
+        return alpha, self.get_mean(X), K_X_inv
+
+    def get_estimate_from_alpha(self, X, X_test, alpha, m_X, K_X_inv=None, Y_test=None):
+        """Posterior mean (and variance when K_X_inv is given) at X_test (reference :137-155)."""
+        spec = self.gp_spec(X.shape[1])
+        if K_X_inv is None:
+            Y_hat = self.get_mean(X_test) + ops.gp_covariance(spec, X_test, X) @ alpha.reshape(-1, 1)
+            var = None
+        else:
+            mean, var = ops.gp_predict([ops.FittedGp(spec, X, alpha, K_X_inv)], X_test)
+            Y_hat, var = mean, var[:, 0]
+        if Y_test is not None:
+            print("MSE:", torch.sum((Y_test - Y_hat) ** 2) / Y_test.size()[0])
+        return Y_hat if var is None else (Y_hat, var)
+
+    def get_estimate(self, X, Y, X_test, Y_test=None, flg_return_K_X_inv=False):
+        """Fit on (X, Y), predict at X_test (reference :157-171)."""
+        alpha, m_X, K_X_inv = self.get_alpha(X, Y)
+        Y_hat, var = self.get_estimate_from_alpha(X, X_test, alpha, m_X, K_X_inv=K_X_inv, Y_test=Y_test)
+        if flg_return_K_X_inv:
+            return Y_hat, var, alpha, m_X, K_X_inv
+        return Y_hat, var, alpha
+
+    def get_SOD(self, X, Y, threshold, flg_permutation=False):
+        """Greedy subset of data: a point joins the subset when the predictive std of the GP fitted on the current
+        subset exceeds `threshold` at it (reference :232-257).  Every refit / prediction is a native call; the
+        threshold test is the one host sync per candidate."""
+        n = X.shape[0]
+        rest = (1 + torch.randperm(n - 1)).tolist() if flg_permutation else list(range(1, n))
+        order = [0] + rest  # the first sample always seeds the subset
+        chosen = [0]
+        thr = float(P._np(threshold).reshape(-1)[0])
+        spec = self.gp_spec(X.shape[1])
+        for i in order[1:]:
+            idx = torch.as_tensor(chosen, device=X.device)
+            alpha, K_inv = ops.gp_precompute(spec, X[idx, :], Y[idx, :])
+            _, var = ops.gp_predict([ops.FittedGp(spec, X[idx, :], alpha, K_inv)], X[i:i + 1, :])
+            if float(torch.sqrt(var[0, 0])) > thr:
+                chosen.append(i)
+        return chosen
+
+    def fit_model(self, *a, **k):
+        raise NotImplementedError("GP hyper-parameter training is outside the rollout hot path (SURVEY.md §8f-2); "
+                                  "train with the reference and load the state_dict")
+
+
+class Combine_GP(GP_prior):
+    """Common part of kernels built from several GP priors (reference :260-296)."""
+
+    def __init__(self, *gp_priors_obj):
+        super().__init__(active_dims=None, sigma_n_num=gp_priors_obj[0].sigma_n_num, dtype=gp_priors_obj[0].dtype,
+                         device=gp_priors_obj[0].device)
+        self.gp_list = torch.nn.ModuleList(gp_priors_obj)
+        self.GP_with_noise = any(gp.GP_with_noise for gp in self.gp_list)
+
+    def to(self, dev):
+        super().to(dev)
+        for gp in self.gp_list:
+            gp.to(dev)
+
+    def print_model(self):
+        for gp in self.gp_list:
+            gp.print_model()
+
+    def get_sigma_n_2(self):
+        s = torch.zeros(1, dtype=self.dtype, device=self.device)
+        for gp in self.gp_list:
+            if gp.GP_with_noise:
+                s = s + gp.get_sigma_n_2()
+        return s
+
+
+class Sum_Independent_GP(Combine_GP):
+    """Sum of independent GP priors: covariances add (reference :299-347).  The prior mean is the FIRST child's only —
+    the reference's get_mean returns from inside its loop (:306-312) — and that is reproduced."""
+
+    def _fill_spec(self, spec):
+        mean0 = None
+        for gp in self.gp_list:
+            m = gp._fill_spec(spec)
+            if mean0 is None:
+                mean0 = m
+        return mean0 or 0.0
+
+
+class Multiply_GP_prior(Combine_GP):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("Multiply_GP_prior is not used by any MC-PILCO configuration and is outside the hot path")
+
+
+def Scale_GP_prior(*a, **k):
+    raise NotImplementedError("Scale_GP_prior is not used by any MC-PILCO configuration and is outside the hot path")

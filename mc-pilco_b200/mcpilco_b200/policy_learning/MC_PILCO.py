@@ -1,0 +1,312 @@
+"""MC-PILCO policy-learning objects — the hot-path part of the reference's `policy_learning/MC_PILCO.py`:
+`MC_PILCO.apply_policy` (:615-674), `MC_PILCO.reinforce_policy` (:375-613), `MC_PILCO.rollout` (:347-373) and
+`MC_PILCO4PMS.apply_policy` (:808-906), with the reference's constructor and method signatures.
+
+`apply_policy` is ONE fused CUDA rollout (libmcpilco_b200.so) instead of a Python loop of torch ops, and it is ONE autograd
+node: `cost.backward()` runs the hand-written backprop-through-time kernel and deposits `.grad` on
+`control_policy.log_lengthscales / centers / f_linear.weight (/ bias)` exactly where the reference's autograd graph would.
+Under `torch.distributed` (one process per GPU) particles are sharded; cost statistics are all-gathered and the policy
+gradient all-reduced inside the same node (mcpilco_b200.distributed).
+
+Out of scope: the trial loop `reinforce`, data collection from the (simulated / real) system, logging
+and log re-loading, `MC_PILCO_Experiment`.  Those are host orchestration the reference keeps doing; see INTEGRATION.md for
+how its classes bind to these methods.
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import _ops as ops
+from .. import _pack as P
+from .. import distributed as D
+
+
+class _ParticleRollout(torch.autograd.Function):
+    """states, inputs, cost, std_cost = rollout(policy parameters).  The graph of the reference (~H*E*40 nodes retaining
+    [M, N] tensors, MC_PILCO.py:522) collapses into this single node with O(M*H*E*D) checkpoints."""
+
+    @staticmethod
+    def forward(ctx, plan, x0, shard, *params):
+        states, inputs = plan.forward(x0)
+        ctx.plan, ctx.shard = plan, shard
+        ctx.want_gx0 = bool(x0.requires_grad)
+        ctx.n_params = len(params)
+        ctx.set_materialize_grads(False)
+        rank, world, group, m_global = shard
+        if plan.cost_out is None:
+            cost = std = torch.zeros((), dtype=states.dtype, device=states.device)
+        elif world == 1:
+            cost, std = plan.cost_out[0].clone(), plan.cost_out[1].clone()
+        else:
+            counts = [D.shard(m_global, r, world)[1] for r in range(world)]
+            mean, m2 = D.merge_cost_stats(D.gather_cost_stats(plan.cost_stats, group, world), counts)
+            cost, std = D.expected_cost_from_stats(mean, m2, m_global)
+        ctx.mark_non_differentiable(std)
+        return states, inputs, cost, std
+
+    @staticmethod
+    def backward(ctx, g_states, g_inputs, g_cost, g_std):
+        plan = ctx.plan
+        rank, world, group, m_global = ctx.shard
+        w_local = plan.M / float(m_global)  # this shard's weight in the global particle mean
+        generic = g_states is not None or g_inputs is not None
+        if generic:
+            gc = 0.0 if g_cost is None else float(g_cost) * w_local
+            gs = None if g_states is None else (g_states * w_local if world > 1 else g_states)
+            gi = None if g_inputs is None else (g_inputs * w_local if world > 1 else g_inputs)
+            gr = plan.backward(grad_cost=gc, grad_states=gs, grad_inputs=gi, want_gx0=ctx.want_gx0)
+            scale = None
+        else:
+            if g_cost is None:
+                return (None,) * (3 + ctx.n_params)
+            gr = plan.backward(grad_cost=w_local, want_gx0=ctx.want_gx0)
+            scale = g_cost  # stays on the device: no host sync
+        keys = ["log_ls", "centers", "W"] + (["bias"] if ctx.n_params == 4 else [])
+        if world > 1:
+            flat = torch.cat([gr[k].reshape(-1) for k in keys])
+            D.allreduce_sum_(flat, group)
+            off = 0
+            for k in keys:
+                n = gr[k].numel()
+                gr[k] = flat[off:off + n].view_as(gr[k])
+                off += n
+        out = [gr[k] if scale is None else gr[k] * scale for k in keys]
+        gx0 = gr["x0"] if ctx.want_gx0 else None
+        if gx0 is not None and scale is not None:
+            gx0 = gx0 * scale
+        return (None, gx0, None) + tuple(out)
+
+
+class MC_PILCO(torch.nn.Module):
+    """Monte-Carlo Probabilistic Inference for Learning COntrol — hot-path methods (reference :29-751)."""
+
+    def __init__(self, T_sampling, state_dim, input_dim, f_sim, f_model_learning, model_learning_par, f_rand_exploration_policy,
+                 rand_exploration_policy_par, f_control_policy, control_policy_par, f_cost_function, cost_function_par,
+                 std_meas_noise=None, log_path=None, dtype=torch.float64, device=torch.device("cuda")):
+        super().__init__()
+        self.T_sampling, self.dtype, self.device = T_sampling, dtype, device
+        self.state_dim, self.input_dim = state_dim, input_dim
+        self.f_sim = f_sim  # the simulated / real system lives outside this path
+        self.std_meas_noise = np.zeros(state_dim) if std_meas_noise is None else std_meas_noise
+        self.model_learning = f_model_learning(**model_learning_par)
+        self.rand_exploration_policy = None if f_rand_exploration_policy is None else f_rand_exploration_policy(**rand_exploration_policy_par)
+        self.control_policy = f_control_policy(**control_policy_par)
+        self.cost_function = f_cost_function(**cost_function_par)
+        self.state_samples_history, self.input_samples_history, self.noiseless_states_history = [], [], []
+        self.num_data_collection = 0
+        self.log_path = log_path
+        if log_path is not None:
+            self.log_dict = {}
+        self._trial_index = None
+        self._seed_base = None
+        self._rollouts = 0
+
+    # ---- noise bookkeeping ---------------------------------------------------------------------------------------------
+    def _next_seed(self):
+        """Philox key of the next rollout: a base drawn once from torch's RNG (rank 0's, under torch.distributed) plus a
+        rollout counter, so every rank uses the same key and `torch.manual_seed` makes runs reproducible."""
+        if self._seed_base is None:
+            base = torch.randint(0, 2 ** 60, (1,), dtype=torch.int64)
+            rank, world, group = D.world()
+            if world > 1:
+                b = base.to(self.device)
+                torch.distributed.broadcast(b, src=0, group=group)
+                base = b.cpu()
+            self._seed_base = int(base.item())
+        self._rollouts += 1
+        return (self._seed_base + 0x9E3779B97F4A7C15 * self._rollouts) & ((1 << 64) - 1)
+
+    def _initial_particles(self, mean, var, flg_uniform, up, low, flg_multi, count, offset, seed, noise):
+        """Initial particle cloud (reference :635-657): Gaussian, uniform or multi-modal Gaussian."""
+        dev = self.device
+        as_dev = lambda v: torch.as_tensor(v, dtype=self.dtype, device=dev)  # noqa: E731
+        if noise is not None and noise.get("x0") is not None:
+            return as_dev(noise["x0"])
+        if flg_uniform:
+            return ops.init_particles("uniform", as_dev(low).reshape(1, -1), as_dev(up).reshape(1, -1), count, seed, offset)
+        mean, std = as_dev(mean), torch.sqrt(as_dev(var))
+        if noise is not None and noise.get("eps0") is not None and not flg_multi:
+            return mean.reshape(1, -1) + std.reshape(1, -1) * as_dev(noise["eps0"])
+        if not flg_multi:
+            mean, std = mean.reshape(1, -1), std.reshape(1, -1)
+        return ops.init_particles("gauss", mean, std, count, seed, offset)
+
+    def _meas_struct(self):
+        return None
+
+    # ---- the particle rollout ------------------------------------------------------------------------------------------
+    def apply_policy(self, particles_initial_state_mean, particles_initial_state_var, flg_particles_init_uniform,
+                     particles_init_up_bound, particles_init_low_bound, flg_particles_init_multi_gauss, num_particles, T_control,
+                     p_dropout=0.0, _noise=None):
+        """Simulate `num_particles` particles for `T_control` steps under the current policy (reference :615-674).
+        Returns states [H, M_local, Ds] and inputs [H, M_local, Du] (M_local = num_particles unless sharded over ranks).
+        `_noise` (tests only) injects {"x0" | "eps0", "eps", "masks", "meas_eps"} instead of the Philox streams."""
+        H, Ds, Du = int(T_control), self.state_dim, self.input_dim
+        pol, ml = self.control_policy, self.model_learning
+        rank, world, group = D.world()
+        offset, count = D.shard(num_particles, rank, world)
+        seed = self._next_seed()
+        x0 = self._initial_particles(particles_initial_state_mean, particles_initial_state_var, flg_particles_init_uniform,
+                                     particles_init_up_bound, particles_init_low_bound, flg_particles_init_multi_gauss, count, offset,
+                                     seed, _noise)
+        params = [pol.log_lengthscales, pol.centers, pol.f_linear.weight] + ([pol.f_linear.bias] if pol.flg_bias else [])
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x0.requires_grad)
+        fused = self.cost_function.fused_spec(Ds, H, self._trial_index) if hasattr(self.cost_function, "fused_spec") else None
+        cst, ctraj = fused if fused is not None else (None, None)
+        if ctraj is not None:
+            ctraj = torch.as_tensor(ctraj, dtype=self.dtype, device=self.device)
+        nz = _noise or {}
+        plan = ops.RolloutPlan(ml.rollout_model_struct(Ds, Du), ml.fitted_gps(), pol.policy_struct(), pol.policy_tensors(), cost=cst,
+                               cost_traj=ctraj, meas=self._meas_struct(), M=count, H=H, p_dropout=p_dropout, seed=seed,
+                               particle_offset=offset, need_grad=need_grad, eps=nz.get("eps"), masks=nz.get("masks"),
+                               meas_eps=nz.get("meas_eps"), device=x0.device)
+        states, inputs, cost, std = _ParticleRollout.apply(plan, x0, (rank, world, group, int(num_particles)), *params)
+        if fused is not None:
+            key = self._trial_index if getattr(self.cost_function, "flg_var_lengthscales", False) else None
+            states._mcp_fused_cost = (self.cost_function, key, cost, std)
+        return states, inputs
+
+    def rollout(self, data_collection_index, T_rollout=None, particle_pred=False):
+        """Open-loop model rollout along a recorded input trajectory (reference :347-373): one particle, mean prediction."""
+        st = self.state_samples_history[data_collection_index]
+        T_rollout = st.shape[0] if T_rollout is None else T_rollout
+        x = torch.tensor(st[0:1, :], dtype=self.dtype, device=self.device)
+        u = torch.tensor(self.input_samples_history[data_collection_index], dtype=self.dtype, device=self.device)
+        traj = torch.zeros([T_rollout, self.state_dim], dtype=self.dtype, device=self.device)
+        traj[0:1, :] = x
+        with torch.no_grad():
+            for t in range(1, T_rollout):
+                traj[t:t + 1, :], _, _ = self.model_learning.get_next_state(current_state=traj[t - 1:t, :], current_input=u[t - 1:t, :],
+                                                                            particle_pred=particle_pred)
+        return traj.cpu().numpy()
+
+    # ---- the optimisation loop -----------------------------------------------------------------------------------------
+    def reinforce_policy(self, T_control, num_particles, trial_index, particles_initial_state_mean, particles_initial_state_var,
+                         flg_particles_init_uniform, particles_init_up_bound, particles_init_low_bound, flg_particles_init_multi_gauss,
+                         opt_steps_list, lr_list, f_optimizer, num_step_print=10, policy_reinit_dict=None, p_dropout_list=None,
+                         std_cost_filt_order=None, std_cost_filt_cutoff=None, max_std_cost=None, alpha_cost=0.99, alpha_input=0.99,
+                         alpha_diff_cost=0.99, lr_reduction_ratio=0.5, lr_min=0.001, p_drop_reduction=0.0, min_diff_cost=0.1,
+                         num_min_diff_cost=200, min_step=np.inf):
+        """Gradient-based policy improvement on the particle cost (reference :375-613): optimiser built from the eval'd
+        `f_optimizer` string, NaN re-sampling (<= 10 attempts) and policy re-initialisation, exponential monitors of the cost
+        decrease driving learning-rate halving, dropout reduction and early exit."""
+        H = int(T_control / self.T_sampling)
+        n_steps = opt_steps_list[trial_index]
+        p_drop0 = 0.0 if p_dropout_list is None else p_dropout_list[trial_index]
+        self._trial_index = trial_index
+        init = dict(particles_initial_state_mean=particles_initial_state_mean, particles_initial_state_var=particles_initial_state_var,
+                    flg_particles_init_uniform=flg_particles_init_uniform, flg_particles_init_multi_gauss=flg_particles_init_multi_gauss,
+                    particles_init_up_bound=particles_init_up_bound, particles_init_low_bound=particles_init_low_bound,
+                    num_particles=num_particles, T_control=H)
+        f_optim = eval(f_optimizer)
+
+        def sample(p_drop):
+            """Rollout + cost, re-sampled up to 10 times while the cost is NaN; returns (states, inputs, cost, std, still_nan)."""
+            for _ in range(10):
+                states, inputs = self.apply_policy(p_dropout=p_drop, **init)
+                cost, std = self.cost_function(states, inputs, trial_index)
+                if not bool(torch.isnan(cost)):
+                    return states, inputs, cost, std, False
+            return states, inputs, cost, std, True
+
+        def fresh():
+            z = lambda n: torch.zeros(n, device=self.device, dtype=self.dtype)  # noqa: E731
+            return dict(cost=z(n_steps), std=z(n_steps), es1=z(n_steps + 1), es2=0.0, ratio=z(n_steps + 1), lr=lr_list[trial_index],
+                        p_drop=p_drop0, min_diff=min_diff_cost, min_step=min_step, prev=0.0, step=0, done=0)
+
+        with torch.no_grad():  # cost level before optimisation: initialises the cost-difference filter
+            for _ in range(10):
+                st0, in0 = self.apply_policy(p_dropout=p_drop0, **init)
+                cost0, _ = self.cost_function(st0, in0, trial_index)
+                if not bool(torch.isnan(cost0)):
+                    break
+                print("\nSE filter initialization: Cost is NaN - reinit the policy")
+                self.control_policy.reinit(**policy_reinit_dict)
+            del st0, in0
+        s = fresh()
+        cost_tm1 = cost0
+        optimizer = f_optim(p=self.control_policy.parameters(), lr=s["lr"])
+        reinit_counter, t_start = 0, time.time()
+        a = alpha_diff_cost
+        while s["step"] < n_steps:
+            optimizer.zero_grad()
+            states, inputs, cost, std, is_nan = sample(s["p_drop"])
+            k = s["step"]
+            s["cost"][k], s["std"][k] = cost.detach(), std.detach()
+            with torch.no_grad():
+                dc = cost - cost_tm1
+                s["es1"][k + 1] = a * s["es1"][k] + (1 - a) * dc
+                s["es2"] = a * (s["es2"] + (1 - a) * (dc - s["es1"][k]) ** 2)
+                cost_tm1 = s["cost"][k]
+                s["ratio"][k + 1] = a * s["ratio"][k] + (1 - a) * (s["es1"][k + 1] / s["es2"].sqrt())
+            cost.backward()
+            optimizer.step()
+            if k % num_step_print == 0:
+                c = float(cost.detach())
+                print("\nOptimization step:", k, "| cost:", c, "| improvement:", s["prev"] - c, "| p_dropout:", s["p_drop"],
+                      "| diff_cost_ratio:", float(torch.abs(s["ratio"][k + 1])), "| time:", time.time() - t_start)
+                s["prev"], t_start = c, time.time()
+            if k > s["min_step"]:
+                window = torch.abs(s["ratio"][k + 1 - num_min_diff_cost:k + 1]) < s["min_diff"]
+                if int(window.sum()) >= num_min_diff_cost:
+                    if s["lr"] > lr_min:
+                        s["lr"] = max(s["lr"] * lr_reduction_ratio, lr_min)
+                        s["min_diff"] = max(s["min_diff"] / 2, 0.01)
+                        s["min_step"] = k + num_min_diff_cost
+                        optimizer = f_optim(p=self.control_policy.parameters(), lr=s["lr"])
+                        s["p_drop"] = max(s["p_drop"] - p_drop_reduction, 0.0)
+                        print("\nstep", k, ": learning rate ->", s["lr"], ", p_dropout ->", s["p_drop"])
+                    else:
+                        print("\nEXIT FROM OPTIMIZATION: diff_cost_ratio < min_diff_cost for num_min_diff_cost steps")
+                        s["step"] = n_steps
+            s["step"] += 1
+            s["done"] += 1
+            if is_nan:  # ten NaN rollouts in a row: new random policy, restart the optimisation
+                reinit_counter += 1
+                print("\nCost is NaN: re-initialize control policy [attempt #" + str(reinit_counter) + "]")
+                self.control_policy.reinit(**policy_reinit_dict)
+                s = fresh()
+                optimizer = f_optim(p=self.control_policy.parameters(), lr=s["lr"])
+        n = s["done"]
+        return (s["cost"][:n].cpu().numpy(), s["std"][:n].cpu().numpy(), states.detach().cpu().numpy(), inputs.detach().cpu().numpy())
+
+    # ---- host orchestration that stays with the reference --------------------------------------------------------------
+    def _out_of_scope(self, *a, **k):
+        raise NotImplementedError("trial loop / data collection / logging are host orchestration outside the rollout hot path; the "
+                                  "reference's own MC_PILCO keeps them and binds to apply_policy / reinforce_policy (INTEGRATION.md)")
+
+    reinforce = get_data_from_system = get_model_learning_performance = get_rollout_prediction_performance = _out_of_scope
+    load_policy_from_log = load_model_from_log = _out_of_scope
+
+
+class MC_PILCO4PMS(MC_PILCO):
+    """MC-PILCO for partially measurable systems (reference :754-962): inside the rollout the policy sees a simulated
+    measurement — noisy positions, finite-difference velocities, first-order Butterworth low-pass — while the cost is taken on
+    the true states.  Differences from the reference: `std_meas_noise_sim` is honoured when given (the reference only assigns the
+    attribute when the argument is None, :805-806, and would raise AttributeError otherwise)."""
+
+    def __init__(self, T_sampling, state_dim, input_dim, f_sim, f_model_learning, model_learning_par, f_rand_exploration_policy,
+                 rand_exploration_policy_par, f_control_policy, control_policy_par, f_cost_function, cost_function_par, pos_indeces,
+                 vel_indeces, std_meas_noise=None, log_path=None, filtering_dict={}, std_meas_noise_sim=None, dtype=torch.float64,
+                 device=torch.device("cuda")):
+        super().__init__(T_sampling=T_sampling, state_dim=state_dim, input_dim=input_dim, f_sim=f_sim, f_model_learning=f_model_learning,
+                         model_learning_par=model_learning_par, f_rand_exploration_policy=f_rand_exploration_policy,
+                         rand_exploration_policy_par=rand_exploration_policy_par, f_control_policy=f_control_policy,
+                         control_policy_par=control_policy_par, f_cost_function=f_cost_function, cost_function_par=cost_function_par,
+                         std_meas_noise=std_meas_noise, log_path=log_path, dtype=dtype, device=device)
+        self.filtering_dict = filtering_dict
+        self.pos_indeces, self.vel_indeces = pos_indeces, vel_indeces
+        self.std_meas_noise_sim = self.std_meas_noise if std_meas_noise_sim is None else std_meas_noise_sim
+
+    def _meas_struct(self):
+        std_pos = np.asarray(self.std_meas_noise_sim, dtype=np.float64)[list(self.pos_indeces)]
+        return P.meas_struct(self.pos_indeces, self.vel_indeces, std_pos, self.filtering_dict["fc"], self.T_sampling)
+
+    def apply_policy(self, particles_initial_state_mean, particles_initial_state_var, flg_particles_init_uniform,
+                     particles_init_up_bound, particles_init_low_bound, flg_particles_init_multi_gauss, num_particles, T_control,
+                     p_dropout=0.0, _noise=None):
+        """Rollout with the measurement model in the loop (reference :808-906)."""
+        return super().apply_policy(particles_initial_state_mean, particles_initial_state_var, flg_particles_init_uniform,
+                                    particles_init_up_bound, particles_init_low_bound, flg_particles_init_multi_gauss, num_particles,
+                                    T_control, p_dropout=p_dropout, _noise=_noise)

@@ -40,73 +40,10 @@ def _import_reference():
     return types.SimpleNamespace(ML=ML, CF=CF, MCP=MCP, PO=PO)
 
 
-T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+import api_builders as AB  # noqa: E402
+
 CPU = torch.device("cpu")
-
-
-def build_model(R, sc):
-    D = sc["D"]
-    dicts = []
-    for g in sc["gps"]:
-        rbf = dict(active_dims=np.arange(D), lengthscales_init=np.exp(g["log_ls"]), flg_train_lengthscales=True,
-                   lambda_init=np.array([g["lambda"]]), flg_train_lambda=False, sigma_n_init=np.array([g["sigma_n"]]),
-                   flg_train_sigma_n=True, mean_init=np.array([g["mean"]]), sigma_n_num=None, dtype=torch.float64, device=CPU)
-        if g["mpk"]:
-            mpk = dict(active_dims=np.arange(D), poly_deg=len(g["mpk"]), Sigma_pos_par_init_list=list(g["mpk"]),
-                       flg_train_Sigma_pos_par_list=[True] * len(g["mpk"]), dtype=torch.float64, device=CPU)
-            dicts.append([rbf, mpk])
-        else:
-            dicts.append(rbf)
-    m = sc["model"]
-    has_mpk = bool(sc["gps"][0]["mpk"])
-    if m["kind"] == "speed":
-        cls = R.ML.Speed_Model_learning_RBF_MPK_angle_state if has_mpk else R.ML.Speed_Model_learning_RBF_angle_state
-        ml = cls(num_gp=sc["E"], init_dict_list=dicts, T_sampling=m["T"], angle_indeces=m["angle"],
-                 not_angle_indeces=m["not_angle"], vel_indeces=m["vel"], not_vel_indeces=m["pos"])
-    else:
-        ml = R.ML.Model_learning_RBF(num_gp=sc["E"], init_dict_list=dicts)
-    ml.gp_inputs = T(sc["X"])
-    ml.gp_output_list = [T(sc["Y"][:, e:e + 1]) for e in range(sc["E"])]
-    ml.dim_state, ml.dim_input, ml.num_samples = sc["Ds"], sc["Du"], sc["N"]
-    with torch.no_grad():
-        for e in range(sc["E"]):
-            ml.pretrain_gp(e)
-    ml.set_eval_mode()
-    return ml
-
-
-def policy_kwargs(sc):
-    p = sc["policy"]
-    kw = dict(input_dim=sc["Du"], num_basis=p["nb"], lengthscales_init=p["lengthscales"], centers_init=p["centers"],
-              weight_init=p["weight"], flg_squash=p["u_max"] is not None, u_max=p["u_max"] if p["u_max"] is not None else 1,
-              flg_drop=True, flg_bias=p["bias"] is not None, bias_init=p["bias"])
-    if p["kind"] == "angles":
-        kw.update(state_dim=sc["Ds"], angle_indices=p["angle"], non_angle_indices=p["non_angle"])
-    elif p["kind"] == "target":
-        kw.update(state_dim=2 * sc["Ds"], target_traj=p["target_traj"])
-    else:
-        kw.update(state_dim=sc["Ds"], scale_factor=p["scale"])
-    return kw
-
-
-def build_policy(R, sc):
-    cls = {"angles": R.PO.Sum_of_gaussians_with_angles, "target": R.PO.Sum_of_gaussians_with_target_trajectory,
-           "plain": R.PO.Sum_of_gaussians}[sc["policy"]["kind"]]
-    pol = cls(**policy_kwargs(sc))
-    if sc["policy"]["bias"] is not None:
-        pol.f_linear.bias.data = T(sc["policy"]["bias"])
-    return pol
-
-
-def cost_spec(R, sc):
-    c = sc["cost"]
-    if c["kind"] == "cart_pole":
-        return R.CF.Cart_pole_cost, dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), angle_index=c["angle_index"], pos_index=c["pos_index"])
-    if c["kind"] == "sat_traj":
-        return R.CF.Expected_saturated_distance_from_trajectory, dict(target_traj=T(c["target_traj"]), lengthscales=T(c["ls"]))
-    if c["kind"] == "sat_target":
-        return R.CF.Expected_saturated_distance, dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), active_dims=c["active"])
-    raise KeyError(c["kind"])
+T = AB.tensor_factory(CPU)
 
 
 class Feeder:
@@ -121,10 +58,10 @@ class Feeder:
         return x
 
 
-def run_scenario(R, name):
+def run_scenario(R, name, save=True):
     sc = scenarios.scenario(name)
     out = {}
-    ml = build_model(R, sc)
+    ml = AB.build_model(R, sc, CPU)
     rs = np.random.RandomState(7)
     Xs = T(sc["X"][:5] + 0.1 * rs.randn(5, sc["D"]))
     out["Xs"] = Xs.numpy()
@@ -143,18 +80,7 @@ def run_scenario(R, name):
         out["sod_thr_0"] = thr.detach().numpy()
 
     # ---- full rollout through the reference's apply_policy ----
-    cost_cls, cost_par = cost_spec(R, sc)
-    common = dict(T_sampling=sc["model"]["T"] or 0.05, state_dim=sc["Ds"], input_dim=sc["Du"], f_sim=None,
-                  f_model_learning=lambda: ml, model_learning_par={}, f_rand_exploration_policy=R.PO.Random_exploration,
-                  rand_exploration_policy_par=dict(state_dim=sc["Ds"], input_dim=sc["Du"]),
-                  f_control_policy=lambda: build_policy(R, sc), control_policy_par={}, f_cost_function=cost_cls,
-                  cost_function_par=cost_par)
-    if "pms" in sc:
-        obj = R.MCP.MC_PILCO4PMS(pos_indeces=sc["pms"]["pos_idx"], vel_indeces=sc["pms"]["vel_idx"],
-                                 filtering_dict={"fc": sc["pms"]["fc"]},
-                                 std_meas_noise=np.array([sc["pms"]["std_pos"][0], 0.0, sc["pms"]["std_pos"][1], 0.0]), **common)
-    else:
-        obj = R.MCP.MC_PILCO(**common)
+    obj = AB.build_pilco(R, sc, ml, CPU, rand_policy=R.PO.Random_exploration)
     pol = obj.control_policy
     M, H, nb, p = sc["M"], sc["H"], sc["policy"]["nb"], sc["p_dropout"]
 
@@ -175,9 +101,7 @@ def run_scenario(R, name):
         mfeed = Feeder([T(sc["meas_eps"][t]) for t in range(H - 1)])
         torch.randn = lambda *shape, **k: mfeed(shape)
     try:
-        states, inputs = obj.apply_policy(particles_initial_state_mean=T(sc["x0_mean"]), particles_initial_state_var=T(sc["x0_var"]),
-                                          flg_particles_init_uniform=False, particles_init_up_bound=None, particles_init_low_bound=None,
-                                          flg_particles_init_multi_gauss=False, num_particles=M, T_control=H, p_dropout=p)
+        states, inputs = obj.apply_policy(**AB.apply_kwargs(sc, CPU))
     finally:
         nrm._standard_normal, mvn._standard_normal, torch.randn = old
     cost, std_cost = obj.cost_function(states, inputs, 0)
@@ -202,9 +126,11 @@ def run_scenario(R, name):
         c = sc["cost"]
         cd, _ = R.CF.Expected_distance(target_state=T(c["target"]), lengthscales=T(c["ls"]), active_dims=c["active"])(st, None)
         out["cost_distance"] = cd.numpy()
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    if save:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "cost", float(cost), "std", float(std_cost), "|g_centers|", float(np.abs(out["g_centers"]).max()),
           "min var", min(float(out[f"pvar_{e}"].min()) for e in range(sc["E"])))
+    return out
 
 
 if __name__ == "__main__":
