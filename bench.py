@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-particles", type=int, default=512)
     ap.add_argument("--cpu-horizon", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     ap.add_argument("--se-only", action="store_true", help="config 2 kernel (pure squared-exponential)")
     return ap.parse_args()
 
@@ -264,11 +265,15 @@ def own_arm(args):
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         cost, std = step()
     e1.record()
     barrier()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler is not None else None
     launches = ops.launch_count(reset=True)

@@ -136,4 +136,8 @@ dgemm_nt_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
 int dgemm_nt(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C,
              int ldc, int tri, int kflags, cudaStream_t st);
 
+// TMA + mbarrier pipelined variant for full (non-triangular) products (mcp_dgemm_tma.cu)
+bool dgemm_tma_usable(const double* A, int lda, const double* B, int ldb, const double* C, int ldc);
+int dgemm_nt_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc, cudaStream_t st);
+
 }  // namespace mcp

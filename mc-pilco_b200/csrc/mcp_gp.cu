@@ -323,7 +323,11 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     const double* xs = Xs + (size_t)m0 * g.spec.D;
     if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
     prof_begin(st);
-    if (int err = dgemm_nt(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, 0.0, V, ldk, 0, 0, st)) return err;
+    if (N >= 256 && dgemm_tma_usable(Ks, ldk, g.Kinv, g.ld_kinv, V, ldk)) {
+      if (int err = dgemm_nt_tma(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, V, ldk, st)) return err;
+    } else {
+      if (int err = dgemm_nt(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, 0.0, V, ldk, 0, 0, st)) return err;
+    }
     prof_end(st, 2.0 * (double)mc * (double)N * (double)N);
     dim3 grid(cdiv(mc, 8));
     double* jm = jac ? jmean + (size_t)m0 * E * g.spec.D : nullptr;
