@@ -626,10 +626,11 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
     size_t n = (size_t)M * H;
     cost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r->cost, M, H, Ds, r->states, r->costs);
     MCP_LAUNCH_CHECK();
-    cost_stats_kernel<<<H, 256, 0, st>>>(M, r->costs, w.stats);
+    double* stats = r->cost_stats ? r->cost_stats : w.stats;  // [H, 2] per-step {mean, M2}: what shards merge across GPUs
+    cost_stats_kernel<<<H, 256, 0, st>>>(M, r->costs, stats);
     MCP_LAUNCH_CHECK();
     if (r->cost_out) {
-      cost_final_kernel<<<1, 32, 0, st>>>(M, H, w.stats, r->cost_out);
+      cost_final_kernel<<<1, 32, 0, st>>>(M, H, stats, r->cost_out);
       MCP_LAUNCH_CHECK();
     }
   }

@@ -309,3 +309,29 @@ def test_posterior_tiles_and_tails(nh, N, M):
     close(q, q_ref.cpu().numpy(), 1e-10)  # N-term sums in different orders (DMMA tiles vs cuBLAS)
     close(var[:, 0], var_ref.cpu().numpy(), 1e-7, 1e-12)
     assert torch.isfinite(jm).all() and torch.isfinite(jv).all()
+
+
+def test_cost_stats_output_and_shard_merge(nh):
+    """The per-step {mean, M2} statistics the rollout exports are what two half-size shards need to rebuild the global
+    Expected_cost (single GPU here: the two shards run one after the other; the collectives are covered by the gloo test)."""
+    from mcpilco_b200 import distributed as D
+    sc, g = scenarios.scenario("c2"), Hh.load_golden("c2")
+    sc = dict(sc); sc["M"] = 1000
+    gps = nh.native_fit(sc, golden=g)
+    x0 = nh.G(sc["x0_mean"]).repeat(sc["M"], 1)
+    full, _ = nh.native_plan(sc, gps, need_grad=False, inject=False, seed=5)
+    full.forward(x0)
+    costs = full.costs
+    close(full.cost_stats[:, 0], costs.mean(1).cpu().numpy(), 1e-13)
+    close(full.cost_stats[:, 1], ((costs - costs.mean(1, keepdim=True)) ** 2).sum(1).cpu().numpy(), 1e-10, 1e-20)
+    stats, counts = [], []
+    for r in range(3):
+        off, cnt = D.shard(sc["M"], r, 3)
+        sh = dict(sc); sh["M"] = cnt
+        plan, _ = nh.native_plan(sh, gps, need_grad=False, inject=False, seed=5, particle_offset=off)
+        plan.forward(x0[off:off + cnt])
+        stats.append(plan.cost_stats.clone()); counts.append(cnt)
+    mean, m2 = D.merge_cost_stats(torch.stack(stats), counts)
+    cost, std = D.expected_cost_from_stats(mean, m2, sc["M"])
+    close(cost, float(full.cost_out[0]), 1e-13)
+    close(std, float(full.cost_out[1]), 1e-10)
