@@ -56,6 +56,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
 }
+// 8-byte async copy global->shared; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, int src_bytes) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -20,7 +20,7 @@
 
 namespace mcp {
 
-constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = 6;
+constexpr int T_BM = 128, T_BN = 128, T_BK = 16, T_STAGES = 6, T_GROUP = 12;
 constexpr int T_TILE_BYTES = T_BM * T_BK * 8;           // 16 KB per operand tile
 constexpr int T_STAGE_BYTES = 2 * T_TILE_BYTES;         // A + B
 constexpr int T_CONSUMER_WARPS = 8;
@@ -67,7 +67,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const unsigned char* tiles = smem_raw + (base - smem_u32(smem_raw));  // same address for ordinary (compiler-scheduled) loads
   const unsigned bars = base + T_STAGES * T_STAGE_BYTES;        // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * T_BM, n0 = blockIdx.x * T_BN;
+  // grouped rasterisation: consecutive CTAs (one wave = 148 of them) cover T_GROUP row blocks x ~148/T_GROUP column blocks, so a
+  // wave pulls ~(12 + 12) operand panels through L2 instead of (2 + 64) with a row-major tile order
+  const int tiles_m = (M + T_BM - 1) / T_BM, tiles_n = (N + T_BN - 1) / T_BN;
+  const int per_group = T_GROUP * tiles_n, group = blockIdx.x / per_group, first_m = group * T_GROUP;
+  const int rows_here = min(tiles_m - first_m, T_GROUP), in_group = blockIdx.x - group * per_group;
+  const int m0 = (first_m + in_group % rows_here) * T_BM, n0 = (in_group / rows_here) * T_BN;
   const int KT = (K + T_BK - 1) / T_BK;
 
   if (threadIdx.x == 0) {
@@ -211,7 +216,7 @@ int dgemm_nt_tma(int M, int N, int K, double alpha, const double* A, int lda, co
   CUtensorMap tmA, tmB;
   if (int e = make_map(&tmA, A, M, K, lda)) return e;
   if (int e = make_map(&tmB, B, N, K, ldb)) return e;
-  dim3 grid(cdiv(N, T_BN), cdiv(M, T_BM));
+  dim3 grid((unsigned)cdiv(N, T_BN) * (unsigned)cdiv(M, T_BM));
   dgemm_tma_kernel<<<grid, T_THREADS, T_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, alpha, C, ldc);
   MCP_LAUNCH_CHECK();
   return MCP_OK;

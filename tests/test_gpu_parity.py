@@ -303,7 +303,7 @@ def test_posterior_tiles_and_tails(nh, N, M):
     mean_ref = 0.02 + Ks @ alpha
     q_ref = (V * Ks).sum(1)
     var_ref = ops.gp_diag_covariance(spec, Xs) - q_ref
-    close(mean, mean_ref.cpu().numpy(), 1e-10, 1e-12)
+    close(mean, mean_ref.cpu().numpy(), 1e-10, 1e-10)  # |alpha| ~ 1e2..1e3 over N terms: absolute rounding floor
     # the quadratic form itself agrees to rounding; var = k** - q inherits the cancellation (var/k** ~ 1e-2..1e-4 here)
     q = ops.gp_diag_covariance(spec, Xs) - var[:, 0]
     close(q, q_ref.cpu().numpy(), 1e-10)  # N-term sums in different orders (DMMA tiles vs cuBLAS)
