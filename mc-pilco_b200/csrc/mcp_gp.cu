@@ -576,7 +576,8 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     const double* xs = Xs + (size_t)m0 * g.spec.D;
     if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
     prof_begin(st);
-    if (N >= 256 && dgemm_tma_usable(Ks, ldk, g.Kinv, g.ld_kinv, V, ldk)) {
+    // the TMA kernel's 128 x 128 tiles need enough of them to fill the GPU; below that the small-tile cp.async kernel wins
+    if ((size_t)cdiv(mc, 128) * cdiv(N, 128) >= 96 && dgemm_tma_usable(Ks, ldk, g.Kinv, g.ld_kinv, V, ldk)) {
       if (int err = dgemm_nt_tma(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, V, ldk, st)) return err;
     } else {
       if (int err = dgemm_nt(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, 0.0, V, ldk, 0, 0, st)) return err;

@@ -284,7 +284,7 @@ def P_bad_spec(nh):
     return s  # lengthscales so long that K is numerically rank one and sigma_n = 0: Cholesky breaks down
 
 
-@pytest.mark.parametrize("N,M", [(300, 77), (257, 130), (1000, 513), (4096, 300)])
+@pytest.mark.parametrize("N,M", [(300, 77), (257, 130), (1000, 513), (4096, 300), (2003, 800)])
 def test_posterior_tiles_and_tails(nh, N, M):
     """TMA-pipelined FP64 tensor-core contraction at ragged sizes (row / column / K tails are zero-filled by the TMA unit):
     posterior from the CUDA path vs the same formula evaluated with torch fp64 matmul on the CUDA covariance matrices."""
