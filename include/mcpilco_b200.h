@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 2
+#define MCP_ABI_VERSION 3
 
 #define MCP_MAX_D 32    /* gp-input dimension            */
 #define MCP_MAX_DS 16   /* state dimension               */
@@ -198,6 +198,19 @@ int mcpilco_gp_diag_covariance(const McpGpSpec* spec, const double* X, int n, do
 size_t mcpilco_gp_precompute_workspace_bytes(int N);
 int mcpilco_gp_precompute(const McpGpSpec* spec, const double* Xtr, const double* y, int N, double* alpha,
                           double* Kinv, int ld, double* Lfac, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Training objective of the GP hyper-parameters and its analytic gradient:
+ *   out[0] = 0.5 ((y - m)^T K^-1 (y - m) + log det K)   (Marginal_log_likelihood.forward, gpr_lib/Likelihood/Gaussian_likelihood.py:12-24,
+ *   evaluated on GP_prior.forward's outputs, GP_prior.py:91-115; the reference obtains the gradient by autograd through
+ *   torch.cholesky / torch.inverse inside GP_prior.fit_model, GP_prior.py:179-230),
+ *   out[1] = d/d lambda, out[2] = d/d mean0, out[3] = d/d sigma_n2, out[4 + j] = d/d inv_ls[j] (j < MCP_MAX_D),
+ *   out[4 + MCP_MAX_D + (p * MCP_MAX_DEG + f) * (MCP_MAX_D + 1) + j] = d/d poly_w2[p][f][j].
+ * Gradients are with respect to the McpGpSpec fields; the caller applies the chain rule of its parametrisation.
+ * `out` is a DEVICE array of mcpilco_gp_nlml_grad_size() doubles. */
+int mcpilco_gp_nlml_grad_size(void);
+size_t mcpilco_gp_nlml_workspace_bytes(int N);
+int mcpilco_gp_nlml(const McpGpSpec* spec, const double* X, const double* y, int N, double* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* Posterior at M test inputs for E GPs: mean[m,e] = mean0 + K* alpha, var[m,e] = var_scale (k** - k*^T Kinv k*),
  * and (optional) their Jacobians w.r.t. the test input, jmean/jvar [M, E, D].

@@ -14,6 +14,9 @@ from . import _pack as P
 F64 = torch.float64
 
 
+_ws_cache = {}
+
+
 def _need_cuda(t, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != F64:
         raise RuntimeError("mcpilco_b200: %s must be a CUDA float64 tensor (this path has no CPU fallback); got %s"
@@ -95,6 +98,28 @@ def gp_precompute(spec, Xtr, y, want_L=False):
     return out + (Lbuf[:, :n],) if want_L else out
 
 
+def gp_nlml(spec, Xtr, y):
+    """Negative marginal log likelihood and its gradient w.r.t. the McpGpSpec fields, as one device tensor (layout:
+    include/mcpilco_b200.h, mcpilco_gp_nlml).  GP_prior.py:91-115,179-230; Gaussian_likelihood.py:12-24."""
+    Xtr, y = _c(Xtr, "X"), _c(y, "Y").reshape(-1)
+    L_ = _enter(Xtr.device)
+    n = Xtr.shape[0]
+    if n < 1 or Xtr.shape[1] != spec.D or y.numel() != n:
+        raise RuntimeError("gp_nlml: X must be [N>=1, %d] and Y [N, 1]" % spec.D)
+    out = torch.empty(L_.mcpilco_gp_nlml_grad_size(), dtype=F64, device=Xtr.device)
+    wsb = L_.mcpilco_gp_nlml_workspace_bytes(n)
+    ws = _workspace(Xtr.device, wsb, "nlml")
+    N.check(L_.mcpilco_gp_nlml(C.byref(spec), _ptr(Xtr), _ptr(y), n, _ptr(out), _ptr(ws), ws.numel(), _stream(Xtr.device)))
+    return out
+
+
+NLML_LAMBDA, NLML_MEAN, NLML_SN2, NLML_ILS = 1, 2, 3, 4
+
+
+def nlml_poly_offset(p, f):
+    return 4 + N.MAX_D + (p * N.MAX_DEG + f) * (N.MAX_D + 1)
+
+
 def kinv_for_kernels(Kinv):
     """Return (tensor, ld) with a 16-byte aligned base and an even leading dimension; copies only if needed."""
     _need_cuda(Kinv, "K_X_inv")
@@ -133,9 +158,6 @@ def _gp_array(gps):
     for i, g in enumerate(gps):
         g.fill(arr[i])
     return arr
-
-
-_ws_cache = {}
 
 
 def _workspace(dev, nbytes, tag):

@@ -8,9 +8,12 @@ libmcpilco_b200.so (CUDA, float64).  CPU tensors are rejected: there is no fallb
 
 Out of scope here: `fit_model` (hyper-parameter training), `Multiply_GP_prior`, `Scale_GP_prior`.
 """
+import time
+
 import numpy as np
 import torch
 
+from ... import _native as _N
 from ... import _ops as ops
 from ... import _pack as P
 
@@ -59,12 +62,21 @@ class GP_prior(torch.nn.Module):
             print("-", par_name, ":", par_value.data)
 
     # ---- flattening ----------------------------------------------------------------------------------------
-    def _fill_spec(self, spec):
-        """Add this kernel's term(s) to `spec` and return the constant prior mean it contributes."""
+    # A kernel is described ONCE, as differentiable torch expressions of its parameters (`_kernel_terms`); the POD spec the
+    # CUDA kernels take is their value, and the hyper-parameter gradients of the training objective are obtained by pushing
+    # the native gradient w.r.t. the spec fields back through those same expressions (tiny tensors, torch autograd).
+    def _kernel_terms(self, D):
+        """{"inv_ls": Tensor[D] | None, "lam": 0-dim Tensor, "mean": 0-dim Tensor | None, "polys": [Tensor[deg, D + 1], ...]}:
+        k(x,x') = lam exp(-sum_j ((x_j - x'_j) inv_ls_j)^2) + sum_p prod_f (sum_j W_p[f, j] x_j x'_j + W_p[f, D])."""
         raise NotImplementedError()
 
-    def _noise_value(self):
-        return float(P._np(self.get_sigma_n_2()).reshape(-1)[0]) if self.GP_with_noise else 0.0
+    def _noise_term(self):
+        return self.get_sigma_n_2().reshape(()) if self.GP_with_noise else None
+
+    def _scatter(self, values, D, extra=0):
+        """Place per-active-dimension values into a length D (+extra) vector (zeros elsewhere), differentiably."""
+        out = torch.zeros(D + extra, dtype=self.dtype, device=values.device)
+        return out.index_put((self.active_dims.to(values.device),), values)
 
     def gp_spec(self, D):
         """McpGpSpec of this kernel for a D-dimensional gp input; rebuilt only when a parameter changed."""
@@ -72,10 +84,32 @@ class GP_prior(torch.nn.Module):
         hit = self._spec_cache.get("k")
         if hit is not None and hit[0] == key:
             return hit[1]
-        spec = P.new_gp_spec(int(D))
         with torch.no_grad():
-            spec.mean0 = float(self._fill_spec(spec))
-            spec.sigma_n2 = self._noise_value()
+            t = self._kernel_terms(int(D))
+            sn2 = self._noise_term()
+        spec = P.new_gp_spec(int(D))
+        if t.get("inv_ls") is not None:
+            spec.has_se = 1
+            spec.lambda_ = float(t["lam"])
+            for j, v in enumerate(P._np(t["inv_ls"]).reshape(-1)):
+                spec.inv_ls[j] = float(v)
+        polys = t.get("polys", [])
+        if len(polys) > _N.MAX_POLY:
+            raise NotImplementedError("more than %d polynomial terms" % _N.MAX_POLY)
+        for p, W in enumerate(polys):
+            W = P._np(W)
+            if W.shape[0] > _N.MAX_DEG:
+                raise NotImplementedError("polynomial degree above %d" % _N.MAX_DEG)
+            spec.poly_deg[p] = W.shape[0]
+            for f in range(W.shape[0]):
+                for j in range(int(D)):
+                    spec.poly_w2[p][f][j] = float(W[f, j])
+                spec.poly_w2[p][f][_N.MAX_D] = float(W[f, int(D)])
+        spec.n_poly = len(polys)
+        if not spec.has_se and not spec.n_poly:
+            raise RuntimeError("empty kernel")
+        spec.mean0 = float(t["mean"]) if t.get("mean") is not None else 0.0
+        spec.sigma_n2 = float(sn2) if sn2 is not None else 0.0
         self._spec_cache["k"] = (key, spec)
         return spec
 
@@ -95,7 +129,14 @@ class GP_prior(torch.nn.Module):
         return d
 
     def forward(self, X):
-        """(m_X, K_X, K_X^-1, log det K_X) through the blocked Cholesky of the precompute (reference :91-115)."""
+        """(m_X, K_X, K_X^-1, log det K_X) through the blocked Cholesky of the precompute (reference :91-115).  While
+        hyper-parameters are being trained (grad enabled and some parameter requires grad) the four outputs are produced
+        lazily: Marginal_log_likelihood consumes the handle directly and evaluates loss + analytic gradient in one native call."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return PriorOutput(self, X)
+        return self._forward_values(X)
+
+    def _forward_values(self, X):
         spec = self.gp_spec(X.shape[1])
         K_X = ops.gp_covariance(spec, X, None, add_noise=self.GP_with_noise)
         zero = torch.zeros(X.shape[0], 1, dtype=self.dtype, device=X.device)
@@ -147,9 +188,103 @@ class GP_prior(torch.nn.Module):
                 chosen.append(i)
         return chosen
 
-    def fit_model(self, *a, **k):
-        raise NotImplementedError("GP hyper-parameter training is outside the rollout hot path (SURVEY.md §8f-2); "
-                                  "train with the reference and load the state_dict")
+    def nlml(self, X, Y):
+        """0.5 ((Y - m)^T K^-1 (Y - m) + log det K) as a [1, 1] tensor whose backward fills the hyper-parameter gradients."""
+        params = [p for p in self.parameters() if p.requires_grad]
+        return _Nlml.apply(self, X, Y, *params)
+
+    def fit_model(self, trainloader=None, optimizer=None, criterion=None, N_epoch=1, N_epoch_print=1, f_saving_model=None, f_print=None):
+        """Hyper-parameter optimisation (reference :179-230): for every epoch and batch, loss = criterion(self(inputs), labels),
+        backward, optimizer step."""
+        print("\nInitial parameters:")
+        self.print_model()
+        t_start = time.time()
+        for epoch in range(N_epoch):
+            running_loss, n_btc = 0.0, 0
+            optimizer.zero_grad()
+            for inputs, labels in trainloader:
+                optimizer.zero_grad()
+                loss = criterion(self(inputs), labels)
+                loss.backward()
+                optimizer.step()
+                running_loss, n_btc = running_loss + loss.detach(), n_btc + 1
+            if epoch % N_epoch_print == 0:
+                print("\nEPOCH:", epoch)
+                self.print_model()
+                print("Running loss:", float(running_loss) / n_btc, "| time elapsed:", time.time() - t_start)
+                t_start = time.time()
+                if f_saving_model is not None:
+                    f_saving_model(epoch)
+                if f_print is not None:
+                    f_print()
+        print("\nFinal parameters:")
+        self.print_model()
+
+
+class PriorOutput:
+    """Handle returned by GP_prior.forward in training mode.  Unpacks like the reference's 4-tuple (values, no graph);
+    Marginal_log_likelihood takes the fused route through `gp.nlml`."""
+
+    def __init__(self, gp, X):
+        self.gp, self.X = gp, X
+        self._vals = None
+
+    def _values(self):
+        if self._vals is None:
+            with torch.no_grad():
+                self._vals = self.gp._forward_values(self.X)
+        return self._vals
+
+    def __iter__(self):
+        return iter(self._values())
+
+    def __getitem__(self, i):
+        return self._values()[i]
+
+    def __len__(self):
+        return 4
+
+
+class _Nlml(torch.autograd.Function):
+    """loss = NLML(parameters): forward is one native call returning the value and the gradient w.r.t. the spec fields;
+    backward pushes that gradient through the kernel's own `_kernel_terms` expressions."""
+
+    @staticmethod
+    def forward(ctx, gp, X, Y, *params):
+        D = X.shape[1]
+        out = ops.gp_nlml(gp.gp_spec(D), X, Y)
+        ctx.gp, ctx.D, ctx.params = gp, D, params
+        ctx.save_for_backward(out)
+        return out[0].reshape(1, 1).clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        out, = ctx.saved_tensors
+        gp, D = ctx.gp, ctx.D
+        with torch.enable_grad():
+            t = gp._kernel_terms(D)
+            sn2 = gp._noise_term()
+            outs, gouts = [], []
+            if t.get("inv_ls") is not None:
+                outs += [t["inv_ls"], t["lam"].reshape(())]
+                gouts += [out[ops.NLML_ILS:ops.NLML_ILS + D], out[ops.NLML_LAMBDA]]
+            for p, W in enumerate(t.get("polys", [])):
+                rows = []
+                for f in range(W.shape[0]):
+                    o = ops.nlml_poly_offset(p, f)
+                    rows.append(torch.cat([out[o:o + D], out[o + _N.MAX_D:o + _N.MAX_D + 1]]))
+                outs.append(W)
+                gouts.append(torch.stack(rows))
+            if t.get("mean") is not None:
+                outs.append(t["mean"].reshape(()))
+                gouts.append(out[ops.NLML_MEAN])
+            if sn2 is not None:
+                outs.append(sn2)
+                gouts.append(out[ops.NLML_SN2])
+            keep = [(o, go) for o, go in zip(outs, gouts) if o.requires_grad]
+            grads = torch.autograd.grad([o for o, _ in keep], ctx.params, [go.reshape(o.shape) * g.reshape(()) for o, go in keep],
+                                        allow_unused=True)
+        return (None, None, None) + tuple(grads)
 
 
 class Combine_GP(GP_prior):
@@ -182,13 +317,18 @@ class Sum_Independent_GP(Combine_GP):
     """Sum of independent GP priors: covariances add (reference :299-347).  The prior mean is the FIRST child's only —
     the reference's get_mean returns from inside its loop (:306-312) — and that is reproduced."""
 
-    def _fill_spec(self, spec):
-        mean0 = None
-        for gp in self.gp_list:
-            m = gp._fill_spec(spec)
-            if mean0 is None:
-                mean0 = m
-        return mean0 or 0.0
+    def _kernel_terms(self, D):
+        out = {"inv_ls": None, "lam": None, "mean": None, "polys": []}
+        for k, gp in enumerate(self.gp_list):
+            t = gp._kernel_terms(D)
+            if t.get("inv_ls") is not None:
+                if out["inv_ls"] is not None:
+                    raise NotImplementedError("only one squared-exponential term per GP is supported on the CUDA path")
+                out["inv_ls"], out["lam"] = t["inv_ls"], t["lam"]
+            out["polys"] += list(t.get("polys", []))
+            if k == 0:
+                out["mean"] = t.get("mean")  # the first child's mean only (reference :306-312)
+        return out
 
 
 class Multiply_GP_prior(Combine_GP):

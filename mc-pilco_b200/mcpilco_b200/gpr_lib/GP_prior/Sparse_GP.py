@@ -76,23 +76,21 @@ class Linear_GP(GP_prior.GP_prior):
     def get_Sigma_list(self):
         return [self.get_Sigma()]
 
-    def _sigma_diagonals(self):
-        """[diag(Sigma)] of the single factor, on the host; rejects non-diagonal Sigma."""
-        S = P._np(self.get_Sigma())
-        if np.abs(S - np.diag(np.diag(S))).max() != 0.0:
+    def _factor_weights(self, Sigma, D):
+        """One factor's weight row [D + 1] (per input dimension, then the offset) from its Sigma matrix; diagonal Sigma only."""
+        off = Sigma - torch.diag(torch.diagonal(Sigma))
+        if float(off.detach().abs().max()) != 0.0:
             raise NotImplementedError("the CUDA kernels support diagonal Sigma matrices only (diagonal_covariance)")
-        return [np.diag(S)]
+        d = torch.diagonal(Sigma)
+        row = self._scatter(d[:self.num_features], D, extra=1)
+        if self.flg_offset:
+            row = row + torch.nn.functional.one_hot(torch.tensor(D, device=d.device), D + 1).to(d.dtype) * d[self.num_features]
+        return row
 
-    def _fill_spec(self, spec):
+    def _kernel_terms(self, D):
         if not self.flg_no_mean:
             raise NotImplementedError("a linear prior mean phi(X) w is not supported on the CUDA path (all configurations use flg_no_mean)")
-        diags = self._sigma_diagonals()
-        # add_mpk takes log-parameters with the (deg - d) multiplicity folded in: hand it log(sqrt(diag) / (deg - d))
-        deg = len(diags)
-        with np.errstate(divide="ignore"):
-            logp = np.concatenate([np.log(np.sqrt(d) / (deg - i)) for i, d in enumerate(diags)])
-        P.add_mpk(spec, P._np(self.active_dims), deg, self.flg_offset, logp)
-        return 0.0
+        return {"inv_ls": None, "lam": None, "mean": None, "polys": [self._factor_weights(self.get_Sigma(), D).reshape(1, -1)]}
 
 
 class MPK_GP(Linear_GP):
@@ -121,9 +119,9 @@ class MPK_GP(Linear_GP):
     def get_Sigma(self):
         return self.get_Sigma_deg(self.current_deg)
 
-    def _fill_spec(self, spec):
-        P.add_mpk(spec, P._np(self.active_dims), self.poly_deg, self.flg_offset, self.Sigma_pos_par)
-        return 0.0
+    def _kernel_terms(self, D):
+        rows = [self._factor_weights(self.get_Sigma_deg(d), D) for d in range(self.poly_deg)]
+        return {"inv_ls": None, "lam": None, "mean": None, "polys": [torch.stack(rows)]}
 
 
 def get_Volterra_MPK_GP(active_dims, poly_deg, sigma_n_init=None, flg_train_sigma_n=True, Sigma_pos_par_init_list=[],

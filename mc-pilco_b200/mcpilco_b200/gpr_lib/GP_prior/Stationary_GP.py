@@ -27,9 +27,10 @@ class Stationary_GP(GP_prior.GP_prior):
 
     def get_weigted_distances(self, X1, X2):
         """sum_j ((x_j - x'_j)/l_j)^2, recovered from the native SE covariance of a unit-lambda copy of this kernel."""
-        spec = P.new_gp_spec(X1.shape[1])
-        P.add_se(spec, P._np(self.active_dims), self.log_lengthscales_par, 0.0, 0.0)
         from ... import _ops as ops
+        spec = P.new_gp_spec(X1.shape[1])
+        ls = self.log_lengthscales_par if self.flg_ARD else self.log_lengthscales_par.expand(self.num_features)
+        P.add_se(spec, P._np(self.active_dims), ls, 0.0, 0.0)
         return -torch.log(ops.gp_covariance(spec, X1, X2))
 
 
@@ -50,6 +51,9 @@ class RBF(Stationary_GP):
         mean_init = np.zeros(1) if mean_init is None else np.asarray(mean_init, dtype=np.float64)
         self.mean_par = torch.nn.Parameter(torch.tensor(mean_init, dtype=self.dtype, device=self.device), requires_grad=flg_train_mean)
 
-    def _fill_spec(self, spec):
-        P.add_se(spec, P._np(self.active_dims), self.log_lengthscales_par, self.log_lambda_par, 0.0)
-        return float(P._np(self.mean_par).reshape(-1)[0])
+    def _kernel_terms(self, D):
+        inv = torch.exp(-self.log_lengthscales_par).reshape(-1)
+        if not self.flg_ARD:
+            inv = inv.expand(self.num_features)
+        return {"inv_ls": self._scatter(inv, D), "lam": torch.exp(self.log_lambda_par).reshape(()), "mean": self.mean_par.reshape(-1)[0],
+                "polys": []}

@@ -6,8 +6,9 @@ speed-integration subclasses :496-760): `gp_list`, `gp_inputs`, `gp_output_list`
 one-step prediction; both run in libmcpilco_b200.so.  The particle rollout does not call `get_next_state` step by step:
 `MC_PILCO.apply_policy` hands `fitted_gps()` and `rollout_model_struct()` to the fused rollout.
 
-Out of scope: `train_gp*` / `reinforce_model` (hyper-parameter training), the SOR / L1 estimate paths,
-`SP_Speed_Model_learning_Furuta`.
+`reinforce_model` / `train_gp_likelihood` train the hyper-parameters on the marginal likelihood with an analytic
+gradient (one native call per epoch) instead of autograd through a Cholesky.  Out of scope: the SOR / L1
+estimate paths, `SP_Speed_Model_learning_Furuta`.
 """
 import torch
 from torch.distributions.normal import Normal
@@ -122,10 +123,29 @@ class Model_learning(torch.nn.Module):
         print("MSE gp " + str(gp_index) + ": ", torch.mean((Y - Y_hat) ** 2))
 
     def reinforce_model(self, optimization_opt_list=None):
-        raise NotImplementedError("GP hyper-parameter training is outside the rollout hot path (SURVEY.md §8f-2): load trained "
-                                  "state_dicts into gp_list, then call pretrain_gp(i) for each output")
+        """Re-initialise the GPs, train each one's hyper-parameters, then precompute it (reference :149-161)."""
+        self.init_gp_models()
+        for gp_index in range(self.num_gp):
+            self.train_gp(gp_index=gp_index, optimization_opt_dict=optimization_opt_list[gp_index])
+            with torch.no_grad():
+                self.pretrain_gp(gp_index=gp_index)
 
-    train_gp = train_gp_likelihood = train_SOR_gp_likelihood = reinforce_model
+    def train_gp(self, gp_index, optimization_opt_dict):
+        self.train_gp_likelihood(gp_index, optimization_opt_dict)
+
+    def train_gp_likelihood(self, gp_index, optimization_opt_dict):
+        """Full-batch optimisation of one GP's marginal likelihood (reference :398-421); `f_optimizer` is the reference's
+        eval'd string, `criterion` the (mirrored) Marginal_log_likelihood class."""
+        if self.flg_norm:
+            self.norm_list[gp_index] = torch.max(torch.abs(self.gp_output_list[gp_index]))
+        batch = [(self.gp_inputs, self.gp_output_list[gp_index] / self.norm_list[gp_index])]  # one batch = the whole training set
+        f_optim = eval(optimization_opt_dict["f_optimizer"])
+        gp = self.gp_list[gp_index]
+        gp.fit_model(trainloader=batch, optimizer=f_optim(gp.parameters()), criterion=optimization_opt_dict["criterion"](),
+                     N_epoch=optimization_opt_dict["N_epoch"], N_epoch_print=optimization_opt_dict["N_epoch_print"])
+
+    def train_SOR_gp_likelihood(self, gp_index, optimization_opt_dict):
+        raise NotImplementedError("subset-of-regressors training is outside the rollout hot path (and broken upstream)")
 
     # ---- what the fused rollout consumes -----------------------------------------------------------------------------
     def fitted_gps(self):

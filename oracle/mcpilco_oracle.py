@@ -394,3 +394,19 @@ def cartpole_dataset(N, sigma_n, gen):
     nz = sigma_n * torch.randn(N, 2, dtype=F64, generator=gen)
     Y = torch.stack([s1[:, 1] - s[:, 1], s1[:, 3] - s[:, 3]], 1) + nz
     return X, Y
+
+
+# --------------------------------------------------------------------------------------------
+# hyper-parameter training objective
+# --------------------------------------------------------------------------------------------
+def nlml(spec, X, y):
+    """0.5 ((y - m)^T K^-1 (y - m) + log det K), no N log 2 pi term.  Likelihood/Gaussian_likelihood.py:12-24 on the outputs of
+    GP_prior.forward (GP_prior.py:91-115: upper Cholesky, explicit inverse, log det from the factor's diagonal).
+    Differentiable w.r.t. any spec tensor that requires grad (the reference trains through this very graph)."""
+    K = gp_cov(spec, X, None, noise=True)
+    U = torch.linalg.cholesky(K, upper=True)
+    log_det = 2 * torch.sum(torch.log(torch.diag(U)))
+    U_inv = torch.inverse(U)
+    K_inv = U_inv @ U_inv.t()
+    r = y - gp_mean(spec, X)
+    return 0.5 * (r.t() @ (K_inv @ r) + log_det)

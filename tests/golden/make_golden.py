@@ -37,7 +37,8 @@ def _import_reference():
     import policy_learning.Cost_function as CF
     import policy_learning.MC_PILCO as MCP
     import policy_learning.Policy as PO
-    return types.SimpleNamespace(ML=ML, CF=CF, MCP=MCP, PO=PO)
+    import gpr_lib.Likelihood.Gaussian_likelihood as LK
+    return types.SimpleNamespace(ML=ML, CF=CF, MCP=MCP, PO=PO, LK=LK)
 
 
 import api_builders as AB  # noqa: E402
@@ -58,6 +59,30 @@ class Feeder:
         return x
 
 
+def nlml_goldens(R, sc, adam_steps=5, lr=0.01):
+    """Marginal_log_likelihood value and autograd gradient of every trainable hyper-parameter (Gaussian_likelihood.py:12-24 on
+    GP_prior.forward, GP_prior.py:91-115), and the parameters after a few Adam steps of GP_prior.fit_model (GP_prior.py:179-230)."""
+    import io, contextlib
+    out = {}
+    ml = AB.build_model(R, sc, CPU, pretrain=False)
+    crit = R.LK.Marginal_log_likelihood()
+    for e, gp in enumerate(ml.gp_list):
+        X, Y = ml.gp_inputs, ml.gp_output_list[e]
+        loss = crit(gp(X), Y)
+        loss.backward()
+        out[f"nlml_{e}"] = loss.detach().numpy()
+        for nm, p in gp.named_parameters():
+            if p.requires_grad:
+                out[f"nlml_grad_{e}_{nm}"] = p.grad.detach().numpy().copy()
+        opt = torch.optim.Adam(gp.parameters(), lr=lr)
+        with contextlib.redirect_stdout(io.StringIO()):
+            gp.fit_model(trainloader=[(X, Y)], optimizer=opt, criterion=crit, N_epoch=adam_steps, N_epoch_print=100)
+        for nm, p in gp.named_parameters():
+            if p.requires_grad:
+                out[f"fit_{e}_{nm}"] = p.detach().numpy().copy()
+    return out
+
+
 def run_scenario(R, name, save=True):
     sc = scenarios.scenario(name)
     out = {}
@@ -73,6 +98,7 @@ def run_scenario(R, name, save=True):
         out[f"Kinv_{e}"] = ml.K_X_inv_list[e].numpy()
         mu, var = gp.get_estimate_from_alpha(ml.gp_inputs_tr_list[e], Xs, ml.alpha_list[e], ml.m_X_list[e], ml.K_X_inv_list[e])
         out[f"pmean_{e}"], out[f"pvar_{e}"] = mu.detach().numpy(), var.detach().numpy()
+    out.update(nlml_goldens(R, sc))
     if name == "c1":
         thr = 0.5 * torch.sqrt(ml.gp_list[0].get_sigma_n_2())
         with torch.no_grad():

@@ -189,3 +189,56 @@ def test_reinforce_policy_loop(R):
     assert cost_list.shape == (30,) and std_list.shape == (30,) and isinstance(states, np.ndarray)
     assert states.shape == (sc["H"], 64, 4) and inputs.shape == (sc["H"], 64, 1)
     assert cost_list[-5:].mean() < cost_list[:5].mean()
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_marginal_likelihood_and_gradients(R, name):
+    """Marginal_log_likelihood()(gp(X), Y).backward(): value and every hyper-parameter gradient against the reference's autograd."""
+    import mcpilco_b200.gpr_lib.Likelihood.Gaussian_likelihood as LK
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    ml = AB.build_model(R, sc, DEV, pretrain=False)
+    crit = LK.Marginal_log_likelihood()
+    for e, gp in enumerate(ml.gp_list):
+        loss = crit(gp(ml.gp_inputs), ml.gp_output_list[e])
+        assert loss.shape == (1, 1)
+        assert abs(float(loss.detach()) - float(g[f"nlml_{e}"])) < 1e-9 * abs(float(g[f"nlml_{e}"]))
+        loss.backward()
+        names = [nm for nm, p in gp.named_parameters() if p.requires_grad]
+        assert set(f"nlml_grad_{e}_{nm}" for nm in names) == set(k for k in g if k.startswith(f"nlml_grad_{e}_"))
+        for nm, p in gp.named_parameters():
+            if p.requires_grad:
+                ref = g[f"nlml_grad_{e}_{nm}"]
+                assert p.grad.shape == ref.shape and relmax(p.grad, ref) < 1e-6, (nm, relmax(p.grad, ref))
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "delta"])
+def test_fit_model_adam_steps(R, name):
+    """Five Adam epochs of GP_prior.fit_model land on the reference's parameters."""
+    import contextlib, io
+    import mcpilco_b200.gpr_lib.Likelihood.Gaussian_likelihood as LK
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    ml = AB.build_model(R, sc, DEV, pretrain=False)
+    for e, gp in enumerate(ml.gp_list):
+        opt = torch.optim.Adam(gp.parameters(), lr=0.01)
+        with contextlib.redirect_stdout(io.StringIO()):
+            gp.fit_model(trainloader=[(ml.gp_inputs, ml.gp_output_list[e])], optimizer=opt, criterion=LK.Marginal_log_likelihood(), N_epoch=5,
+                         N_epoch_print=100)
+        for nm, p in gp.named_parameters():
+            if p.requires_grad:
+                np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"fit_{e}_{nm}"], rtol=1e-6, atol=1e-7)
+
+
+def test_reinforce_model_trains_and_pretrains(R):
+    """Model_learning.reinforce_model with the reference's option dict: likelihood goes down, the model is ready for rollouts."""
+    import contextlib, io
+    import mcpilco_b200.gpr_lib.Likelihood.Gaussian_likelihood as LK
+    sc = scenarios.scenario("c2")
+    ml = AB.build_model(R, sc, DEV, pretrain=False)
+    crit = LK.Marginal_log_likelihood()
+    before = [float(crit(gp(ml.gp_inputs), ml.gp_output_list[e]).detach()) for e, gp in enumerate(ml.gp_list)]
+    opt = {"f_optimizer": "lambda p : torch.optim.Adam(p, lr=0.01)", "criterion": LK.Marginal_log_likelihood, "N_epoch": 40, "N_epoch_print": 100}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ml.reinforce_model(optimization_opt_list=[opt] * sc["E"])
+    after = [float(crit(gp(ml.gp_inputs), ml.gp_output_list[e]).detach()) for e, gp in enumerate(ml.gp_list)]
+    assert all(a < b for a, b in zip(after, before))
+    assert all(k is not None for k in ml.K_X_inv_list) and ml.alpha_list[0].shape == (sc["N"], 1)

@@ -69,3 +69,20 @@ def test_butter1_matches_scipy():
         b, a = signal.butter(1, fc)
         bo, ao = O.butter1(fc)
         close(bo, b, 1e-12, 1e-15); close(ao, a, 1e-12, 1e-15)
+
+
+@pytest.mark.parametrize("name", scenarios.ALL)
+def test_nlml_and_gradient(name):
+    """Training objective and its hyper-parameter gradients (log-space parameters, as the reference stores them)."""
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    X = T(sc["X"])
+    for e, sp in enumerate(Hh.oracle_specs(sc)):
+        leaves = [sp["se"]["log_ls"].requires_grad_(True), sp["sigma_n_log"].requires_grad_(True)] + [m["log_par"].requires_grad_(True) for m in sp["mpk"]]
+        loss = O.nlml(sp, X, T(sc["Y"][:, e:e + 1]))
+        close(loss.detach(), g[f"nlml_{e}"], 1e-10)
+        grads = torch.autograd.grad(loss.sum(), leaves)
+        pre = "gp_list.0." if sp["mpk"] else ""
+        close(grads[0], g[f"nlml_grad_{e}_{pre}log_lengthscales_par"], 1e-7, 1e-9)
+        close(grads[1], g[f"nlml_grad_{e}_{pre}sigma_n_log"].reshape(()), 1e-7, 1e-9)
+        for k in range(len(sp["mpk"])):
+            close(grads[2 + k], g[f"nlml_grad_{e}_gp_list.1.gp_list.{k}.Sigma_pos_par"], 1e-7, 1e-9)
