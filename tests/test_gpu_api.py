@@ -242,3 +242,66 @@ def test_reinforce_model_trains_and_pretrains(R):
     after = [float(crit(gp(ml.gp_inputs), ml.gp_output_list[e]).detach()) for e, gp in enumerate(ml.gp_list)]
     assert all(a < b for a, b in zip(after, before))
     assert all(k is not None for k in ml.K_X_inv_list) and ml.alpha_list[0].shape == (sc["N"], 1)
+
+
+def test_initial_particle_distributions(R):
+    """Gaussian / uniform / multi-modal Gaussian initial clouds of apply_policy (reference MC_PILCO.py:635-657): moments of the
+    Philox-generated particles, and states[0] is the cloud."""
+    sc = scenarios.scenario("c2")
+    ml = AB.build_model(R, sc, DEV)
+    obj = AB.build_pilco(R, sc, ml, DEV)
+    T = AB.tensor_factory(DEV)
+    M = 200000
+    base = dict(flg_particles_init_uniform=False, particles_init_up_bound=None, particles_init_low_bound=None,
+                flg_particles_init_multi_gauss=False, num_particles=M, T_control=1, p_dropout=0.0)
+    mean, var = T([0.5, -1.0, 2.0, 0.0]), T([1e-2, 4.0, 1e-4, 0.25])
+    with torch.no_grad():
+        st, _ = obj.apply_policy(particles_initial_state_mean=mean, particles_initial_state_var=var, **base)
+    x0 = st[0]
+    assert x0.shape == (M, 4)
+    assert torch.allclose(x0.mean(0), mean, atol=5 * float(var.max().sqrt()) / M ** 0.5)
+    assert torch.allclose(x0.var(0), var, rtol=0.03)
+    z = (x0 - mean) / var.sqrt()
+    assert abs(float((z ** 3).mean())) < 0.03 and abs(float((z ** 4).mean()) - 3.0) < 0.1      # skewness 0, kurtosis 3
+    assert abs(float(torch.corrcoef(z.t())[0, 1])) < 0.01                                   # independent dimensions
+    lo, up = T([-1.0, 0.0, 2.0, -3.0]), T([1.0, 0.5, 2.5, 3.0])
+    kw = dict(base); kw.update(flg_particles_init_uniform=True, particles_init_up_bound=up, particles_init_low_bound=lo)
+    with torch.no_grad():
+        st, _ = obj.apply_policy(particles_initial_state_mean=mean, particles_initial_state_var=var, **kw)
+    x0 = st[0]
+    assert bool((x0 >= lo).all()) and bool((x0 <= up).all())
+    assert torch.allclose(x0.mean(0), (lo + up) / 2, atol=0.02) and torch.allclose(x0.var(0), (up - lo) ** 2 / 12, rtol=0.03)
+    means = T([[0.0, 0.0, 0.0, 0.0], [10.0, 10.0, 10.0, 10.0], [-10.0, 5.0, 0.0, 1.0]])
+    vars_ = T([[1e-2] * 4, [1e-4] * 4, [1.0] * 4])
+    kw = dict(base); kw.update(flg_particles_init_multi_gauss=True)
+    with torch.no_grad():
+        st, _ = obj.apply_policy(particles_initial_state_mean=means, particles_initial_state_var=vars_, **kw)
+    x0 = st[0]
+    mode = torch.cdist(x0, means).argmin(1)
+    frac = torch.bincount(mode, minlength=3).double() / M
+    assert torch.allclose(frac, torch.full((3,), 1 / 3, dtype=torch.float64, device=DEV), atol=0.01)
+    for k in range(3):
+        sel = x0[mode == k]
+        assert torch.allclose(sel.mean(0), means[k], atol=0.02) and torch.allclose(sel.var(0), vars_[k], rtol=0.05)
+
+
+def test_mean_rollout_along_recorded_inputs(R):
+    """MC_PILCO.rollout (reference MC_PILCO.py:347-373): one particle, particle_pred=False, recorded input trajectory — against the
+    oracle's next_state iterated with the same inputs."""
+    from oracle import mcpilco_oracle as O
+    sc, g = scenarios.scenario("c1"), Hh.load_golden("c1")
+    ml = AB.build_model(R, sc, DEV)
+    obj = AB.build_pilco(R, sc, ml, DEV)
+    Tn = 6
+    obj.state_samples_history = [g["states"][:Tn, 0, :]]
+    obj.input_samples_history = [g["inputs"][:Tn, 0, :]]
+    traj = obj.rollout(0)
+    assert traj.shape == (Tn, 4)
+    X = Hh.T(sc["X"])
+    gps = [(sp, X, Hh.T(g[f"alpha_{e}"]), Hh.T(g[f"Kinv_{e}"])) for e, sp in enumerate(Hh.oracle_specs(sc))]
+    x = Hh.T(g["states"][0:1, 0, :])
+    ref = [x]
+    for t in range(1, Tn):
+        x, _, _ = O.next_state(Hh.oracle_model(sc), gps, x, Hh.T(g["inputs"][t - 1:t, 0, :]), None, particle_pred=False)
+        ref.append(x)
+    np.testing.assert_allclose(traj, torch.cat(ref).numpy(), rtol=1e-6, atol=1e-9)
