@@ -512,6 +512,28 @@ struct Workspace {
   int bwd_ctas;
 };
 
+// side streams / events for running the per-output chains of a small rollout concurrently (one set per device)
+struct Fan {
+  cudaStream_t side[MCP_MAX_E];
+  cudaEvent_t fork, join[MCP_MAX_E];
+};
+static Fan* get_fan() {
+  static Fan fans[16];
+  static bool ready[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!ready[dev]) {
+    Fan& f = fans[dev];
+    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int e = 1; e < MCP_MAX_E; e++) {
+      if (cudaStreamCreateWithFlags(&f.side[e], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&f.join[e], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    ready[dev] = true;
+  }
+  return &fans[dev];
+}
+
 static int bwd_grid(int M) {
   int sms = 148;
   int dev = 0;
@@ -588,7 +610,9 @@ using namespace mcp;
 
 extern "C" __attribute__((visibility("default"))) size_t mcpilco_rollout_workspace_bytes(int M, int H, int E, int D, int Nmax, int nb, int Dp, int Du) {
   size_t fixed = fixed_doubles(M, H, E, D, nb, Dp, Du, E, bwd_grid(M)) * sizeof(double);
-  return fixed + mcpilco_gp_predict_workspace_bytes(M, Nmax) + 16384;
+  // small rollouts run their E per-output chains concurrently: one K*/V scratch per output
+  const size_t copies = ((size_t)M * (size_t)(Nmax > 0 ? Nmax : 1) <= ((size_t)1 << 22)) ? (size_t)(E > 0 ? E : 1) : 1;
+  return fixed + copies * mcpilco_gp_predict_workspace_bytes(M, Nmax) + 16384;
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const McpRollout* r, void* stream) {
@@ -598,6 +622,12 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   if (int e = carve(r, w)) return e;
   const int M = r->M, H = r->H, Ds = r->model.Ds, Du = r->model.Du, E = r->model.E, D = r->model.D;
   const bool meas = r->meas.enabled != 0;
+  // fan the per-output chains out over side streams when one chain cannot fill the GPU and every output gets a full-M scratch
+  int nmax = 1;
+  for (int e = 0; e < E; e++) nmax = r->gps[e].N > nmax ? r->gps[e].N : nmax;
+  const size_t per_gp = (w.scratch_doubles / (size_t)E) & ~(size_t)31;
+  const size_t need_gp = 2 * (size_t)M * (size_t)((nmax + 15) / 16 * 16);
+  Fan* fan = (E > 1 && (size_t)M * nmax <= ((size_t)1 << 22) && per_gp >= need_gp) ? get_fan() : nullptr;
   MCP_CUDA(cudaMemcpyAsync(r->states, r->x0, sizeof(double) * (size_t)M * Ds, cudaMemcpyDeviceToDevice, st));
   if (meas) {
     MCP_CUDA(cudaMemcpyAsync(r->pol_in, r->x0, sizeof(double) * (size_t)M * Ds, cudaMemcpyDeviceToDevice, st));
@@ -611,10 +641,26 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
                                                   t < H - 1 ? w.Xs : nullptr);
     MCP_LAUNCH_CHECK();
     if (t == H - 1) break;
-    for (int e = 0; e < E; e++) {
-      if (int err = gp_posterior_chunk(r->gps[e], E, e, w.Xs, M, w.mean, w.var, r->need_grad ? w.jmean : nullptr,
-                                       r->need_grad ? w.jvar : nullptr, w.scratch, w.scratch_doubles, st))
-        return err;
+    if (fan != nullptr) {
+      // small problem: the E per-output chains (K* tile -> contraction -> reduce) are independent; run them side by side
+      MCP_CUDA(cudaEventRecord(fan->fork, st));
+      for (int e = 0; e < E; e++) {
+        cudaStream_t se = e == 0 ? st : fan->side[e];
+        if (e > 0) MCP_CUDA(cudaStreamWaitEvent(se, fan->fork, 0));
+        if (int err = gp_posterior_chunk(r->gps[e], E, e, w.Xs, M, w.mean, w.var, r->need_grad ? w.jmean : nullptr,
+                                         r->need_grad ? w.jvar : nullptr, w.scratch + (size_t)e * per_gp, per_gp, se))
+          return err;
+        if (e > 0) {
+          MCP_CUDA(cudaEventRecord(fan->join[e], se));
+          MCP_CUDA(cudaStreamWaitEvent(st, fan->join[e], 0));
+        }
+      }
+    } else {
+      for (int e = 0; e < E; e++) {
+        if (int err = gp_posterior_chunk(r->gps[e], E, e, w.Xs, M, w.mean, w.var, r->need_grad ? w.jmean : nullptr,
+                                         r->need_grad ? w.jvar : nullptr, w.scratch, w.scratch_doubles, st))
+          return err;
+      }
     }
     integrate_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->model, r->meas, r->noise, M, t, x_t, w.mean, w.var, w.jmean, w.jvar,
                                                    r->states + (size_t)(t + 1) * M * Ds,
