@@ -145,7 +145,8 @@ typedef struct McpNoise {
 typedef struct McpRollout {
   int32_t M, H;
   int32_t need_grad; /* 1: keep per-step Jacobian checkpoints for mcpilco_rollout_bwd */
-  int32_t _pad;
+  int32_t M_global;  /* particle count of the whole (possibly sharded) rollout, 0 = M.  Kernel mappings are chosen from it so that a
+                        shard performs bit-for-bit the arithmetic the unsharded rollout performs on the same particles */
   McpModel model;
   McpPolicy policy;
   McpCost cost;

@@ -556,6 +556,105 @@ __global__ void __launch_bounds__(256) posterior_reduce_fast_kernel(const __grid
   }
 }
 
+// Reduce for WIDE gp inputs (8 < D <= 32; the UR5 model has D = 24) with an SE term and at most one linear term: a lane cannot
+// hold 4 D accumulators, so the gradient sums are done in two stages per tile of 64 training points.  Stage 1, lanes over points:
+// kernel value, mean / q / E0 accumulators and the four per-point coefficients T[n] = (a e, v e, a, v) into shared memory.
+// Stage 2, lanes over (dimension j, channel c) pairs: acc[j][c] += Y[n][j] T[n][c] — no cross-lane reduction at all.
+//   sum_n a_n dk_n/dx_j = -2 ils_j^2 (x_j E0 - acc[j][a e]) + w1_j acc[j][a]        (and the same with v for the variance)
+constexpr int WIDE_TILE = 64;
+__global__ void __launch_bounds__(256) posterior_reduce_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
+                                                                    int M, const double* __restrict__ Xtr,
+                                                                    const double* __restrict__ alpha, int N,
+                                                                    const double* __restrict__ V, int ldv, double var_scale, int E,
+                                                                    int e, double* __restrict__ mean, double* __restrict__ var,
+                                                                    double* __restrict__ jmean, double* __restrict__ jvar) {
+  __shared__ double sY[WIDE_TILE][MCP_MAX_D + 1];  // +1: lanes over points read a column without bank conflicts
+  __shared__ double sA[WIDE_TILE];
+  __shared__ double sT[8][WIDE_TILE][4];
+  __shared__ double sX[8][MCP_MAX_D];
+  __shared__ double sG[8][MCP_MAX_D][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int m = min(blockIdx.x * 8 + warp, M - 1);
+  const bool owner = blockIdx.x * 8 + warp < M;
+  const int D = s.D, np1 = s.n_poly;  // np1 in {0, 1}
+  if (lane < D) sX[warp][lane] = Xs[(size_t)m * D + lane];
+  __syncwarp();
+  double mu = 0.0, q = 0.0, E0a = 0.0, E0v = 0.0;
+  // stage-2 ownership: pair p = lane + 32 r  ->  (j = p / 4, c = p % 4), r < 4 covers D <= 32
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const double* v = V + (size_t)m * ldv;
+  for (int n0 = 0; n0 < N; n0 += WIDE_TILE) {
+    __syncthreads();  // previous tile fully consumed
+    for (int el = tid; el < WIDE_TILE * D; el += 256) {
+      const int i = el / D, j = el - i * D;
+      sY[i][j] = (n0 + i < N) ? Xtr[(size_t)(n0 + i) * D + j] : 0.0;
+    }
+    if (tid < WIDE_TILE) sA[tid] = (n0 + tid < N) ? alpha[n0 + tid] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < WIDE_TILE / 32; h++) {
+      const int i = h * 32 + lane, n = n0 + i;
+      double d2 = 0.0, L1 = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0;
+      for (int j = 0; j < D; j++) {
+        const double xj = sX[warp][j], yj = sY[i][j];
+        const double t = (xj - yj) * s.inv_ls[j];
+        d2 = fma(t, t, d2);
+        if (np1) L1 = fma(s.poly_w2[0][0][j] * xj, yj, L1);
+      }
+      const double ev = s.has_se ? s.lambda * exp(-d2) : 0.0, kv = ev + L1;
+      const double a = sA[i], vn = (n < N) ? v[n] : 0.0;
+      mu = fma(a, kv, mu);
+      q = fma(vn, kv, q);
+      const double ta = a * ev, tv = vn * ev;
+      E0a += ta;
+      E0v += tv;
+      sT[warp][i][0] = ta; sT[warp][i][1] = tv; sT[warp][i][2] = a; sT[warp][i][3] = vn;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int p = lane + 32 * r, j = p >> 2, c = p & 3;
+      if (j < D) {
+        double a2 = acc[r];
+#pragma unroll 8
+        for (int i = 0; i < WIDE_TILE; i++) a2 = fma(sY[i][j], sT[warp][i][c], a2);
+        acc[r] = a2;
+      }
+    }
+  }
+  mu = warp_sum(mu); q = warp_sum(q); E0a = warp_sum(E0a); E0v = warp_sum(E0v);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int p = lane + 32 * r, j = p >> 2, c = p & 3;
+    if (j < D) sG[warp][j][c] = acc[r];
+  }
+  __syncwarp();
+  if (owner && lane < D) {
+    const int j = lane;
+    const double il2 = -2.0 * s.inv_ls[j] * s.inv_ls[j], xj = sX[warp][j], w1 = np1 ? s.poly_w2[0][0][j] : 0.0;
+    const double ga = il2 * (xj * E0a - sG[warp][j][0]) + w1 * sG[warp][j][2];
+    const double gv = il2 * (xj * E0v - sG[warp][j][1]) + w1 * sG[warp][j][3];
+    // d k(x,x) / dx_j for SE + linear: 2 w1_j x_j
+    const double dkd = np1 ? 2.0 * w1 * xj : 0.0;
+    jmean[((size_t)m * E + e) * D + j] = ga;
+    jvar[((size_t)m * E + e) * D + j] = var_scale * (dkd - 2.0 * gv);
+  }
+  if (owner && lane == 0) {
+    double kd = s.has_se ? s.lambda : 0.0;
+    if (np1) {
+      double L = s.poly_w2[0][0][MCP_MAX_D];
+      for (int j = 0; j < D; j++) L = fma(s.poly_w2[0][0][j] * sX[warp][j], sX[warp][j], L);
+      kd += L;
+    }
+    mean[(size_t)m * E + e] = s.mean0 + mu;
+    var[(size_t)m * E + e] = var_scale * (kd - q);
+  }
+}
+
+static bool wide_reduce_ok(const McpGpSpec& s) {
+  return s.D > 8 && s.has_se && (s.n_poly == 0 || (s.n_poly == 1 && s.poly_deg[0] == 1));
+}
+
 static inline int ld16(int n) { return (n + 15) / 16 * 16; }
 
 // posterior of ONE GP for a chunk of particles through scratch [2 x Mc x ld16(N)]
@@ -595,6 +694,9 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
       else if (g.spec.D <= 6) { if (np_ == 0) MCP_FAST_REDUCE(6, 0); else if (np_ == 1) MCP_FAST_REDUCE(6, 1); else MCP_FAST_REDUCE(6, 2); }
       else { if (np_ == 0) MCP_FAST_REDUCE(8, 0); else if (np_ == 1) MCP_FAST_REDUCE(8, 1); else MCP_FAST_REDUCE(8, 2); }
 #undef MCP_FAST_REDUCE
+    } else if (jac && wide_reduce_ok(g.spec)) {
+      posterior_reduce_wide_kernel<<<grid, 256, 0, st>>>(g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e,
+                                                         mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv);
     } else if (jac) {
       MCP_DISPATCH_D(g.spec.D, (posterior_reduce_kernel<DT, true><<<grid, 256, 0, st>>>(
                                    g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E,

@@ -138,6 +138,79 @@ __global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__
   }
 }
 
+// Same policy evaluation for SMALL particle counts (the real MC-PILCO shapes, M = 200..400): one 128-thread block per
+// particle, threads over basis functions, so a few hundred particles still occupy every SM.
+__global__ void __launch_bounds__(128) policy_fwd_block_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
+                                                               const __grid_constant__ McpNoise nz, int M, int t, int tm,
+                                                               const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
+                                                               double* __restrict__ u_t, double* __restrict__ Xs) {
+  __shared__ double s_il[MCP_MAX_DP], s_z[MCP_MAX_DP], s_part[4][MCP_MAX_DU], s_u[MCP_MAX_DU];
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < pol.Dp) {
+    s_il[tid] = exp(-pol.log_ls[tid]);
+    s_z[tid] = policy_feature(pol, pol_in_t + (size_t)m * pol.Ds, t, tid);
+  }
+  __syncthreads();
+  const bool drop = dropout_active(pol, nz);
+  const double keep_scale = drop ? 1.0 / (1.0 - nz.p_dropout) : 1.0;
+  double a[MCP_MAX_DU];
+#pragma unroll
+  for (int k = 0; k < MCP_MAX_DU; k++) a[k] = 0.0;
+  for (int b = tid; b < pol.nb; b += 128) {
+    const double* c = pol.centers + (size_t)b * pol.Dp;
+    double d = 0.0;
+    for (int j = 0; j < pol.Dp; j++) {
+      double r = (s_z[j] - c[j]) * s_il[j];
+      d = fma(r, r, d);
+    }
+    double h = exp(-d);
+    if (drop) h = keep_unit(nz, M, pol.nb, tm, t, m, b) ? h * keep_scale : 0.0;
+#pragma unroll
+    for (int k = 0; k < MCP_MAX_DU; k++)
+      if (k < pol.Du) a[k] = fma(pol.W[(size_t)k * pol.nb + b], h, a[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < MCP_MAX_DU; k++)
+    if (k < pol.Du) {
+      double v = warp_sum(a[k]);
+      if (lane == 0) s_part[w][k] = v;
+    }
+  __syncthreads();
+  if (tid < pol.Du) {
+    double v = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+    if (pol.has_bias) v += pol.bias[tid];
+    if (pol.squash) v = pol.u_max[tid] * tanh(v / pol.u_max[tid]);
+    u_t[(size_t)m * pol.Du + tid] = v;
+    s_u[tid] = v;
+  }
+  __syncthreads();
+  if (Xs != nullptr && tid < mdl.D) {
+    const double* x = x_t + (size_t)m * mdl.Ds;
+    const int j = tid;
+    double f;
+    if (mdl.use_trig) {
+      if (j < mdl.n_na) f = x[mdl.na_idx[j]];
+      else if (j < mdl.n_na + mdl.n_a) f = sin(x[mdl.a_idx[j - mdl.n_na]]);
+      else if (j < mdl.n_na + 2 * mdl.n_a) f = cos(x[mdl.a_idx[j - mdl.n_na - mdl.n_a]]);
+      else f = s_u[j - mdl.n_na - 2 * mdl.n_a];
+    } else {
+      f = (j < mdl.Ds) ? x[j] : s_u[j - mdl.Ds];
+    }
+    Xs[(size_t)m * mdl.D + j] = f;
+  }
+}
+
+// launch the policy evaluation with the mapping that suits the particle count
+static int launch_policy(const McpPolicy& pol, const McpModel& mdl, const McpNoise& nz, int M, int Mg, int t, int tm,
+                         const double* pol_in_t, const double* x_t, double* u_t, double* Xs, cudaStream_t st) {
+  if (Mg <= 2048)  // chosen from the GLOBAL particle count: shards of one rollout must add the basis functions in the same order
+    policy_fwd_block_kernel<<<M, 128, 0, st>>>(pol, mdl, nz, M, t, tm, pol_in_t, x_t, u_t, Xs);
+  else
+    policy_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(pol, mdl, nz, M, t, tm, pol_in_t, x_t, u_t, Xs);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
 // delta = mean + sqrt(var) eps; integrate; checkpoint J = d(delta)/d(gp input); simulated measurement (4PMS).
 // Model_learning.py:685-718 / :471-493; MC_PILCO.py:878-899.
 __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ McpModel mdl, const __grid_constant__ McpMeas ms,
@@ -216,6 +289,73 @@ __global__ void init_particles_kernel(int kind, const double* __restrict__ a, co
     } else {
       Philox4 q = philox4x32_10(seed, (uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)RNG_X0 << 24, (uint32_t)j);
       x0[(size_t)m * Ds + j] = fma(hi - lo, u01(q.v[0], q.v[1]), lo);
+    }
+  }
+}
+
+// The same step with one WARP per particle (lanes over outputs, then over the E x D checkpoint entries): used for small particle
+// counts, where a thread per particle leaves the GPU idle behind a serial E x D loop.
+__global__ void __launch_bounds__(256) integrate_warp_kernel(const __grid_constant__ McpModel mdl, const __grid_constant__ McpMeas ms,
+                                                             const __grid_constant__ McpNoise nz, int M, int t,
+                                                             const double* __restrict__ x_t, const double* __restrict__ mean,
+                                                             const double* __restrict__ var, const double* __restrict__ jmean,
+                                                             const double* __restrict__ jvar, double* __restrict__ x_n,
+                                                             double* __restrict__ jac_t, const double* __restrict__ polin_t,
+                                                             double* __restrict__ polin_n, double* __restrict__ nv) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int E = mdl.E, D = mdl.D, Ds = mdl.Ds;
+  const double* x = x_t + (size_t)m * Ds;
+  double* xn = x_n + (size_t)m * Ds;
+  double delta = 0.0, coef = 0.0;
+  if (lane < E) {
+    const double mu = mean[(size_t)m * E + lane], v = var[(size_t)m * E + lane];
+    delta = mu;
+    if (mdl.particle_pred) {
+      const double eps = nz.eps ? nz.eps[((size_t)t * M + m) * E + lane] : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_EPS, lane);
+      const double sd = sqrt(v);
+      delta = fma(sd, eps, mu);
+      coef = eps / (2.0 * sd);
+    }
+  }
+  if (jac_t) {
+    const size_t base = (size_t)m * E * D;
+    const int n = E * D;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int idx = i0 + lane, e = min(idx, n - 1) / D;
+      const double ce = __shfl_sync(0xffffffffu, coef, e);
+      if (idx < n) jac_t[base + idx] = fma(ce, jvar[base + idx], jmean[base + idx]);
+    }
+  }
+  if (mdl.kind == 1) {
+    if (lane < Ds) xn[lane] = 0.0;  // the reference starts from zeros (Model_learning.py:700)
+    __syncwarp();
+    if (lane < E) {
+      const int iv = mdl.vel_idx[lane], ip = mdl.pos_idx[lane];
+      xn[iv] = x[iv] + delta;
+      xn[ip] = x[ip] + mdl.T * x[iv] + 0.5 * mdl.T * delta;
+    }
+  } else if (lane < E) {
+    xn[lane] = x[lane] + delta;
+  }
+  if (ms.enabled) {
+    __syncwarp();
+    const double* pp = polin_t + (size_t)m * Ds;
+    double* pn = polin_n + (size_t)m * Ds;
+    if (lane < Ds) pn[lane] = xn[lane];
+    __syncwarp();
+    if (lane < ms.n_pos) {
+      const int i = lane, ip = ms.pos_idx[i], iv = ms.vel_idx[i];
+      const double e = nz.meas_eps ? nz.meas_eps[((size_t)t * M + m) * ms.n_pos + i]
+                                   : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_MEAS, i);
+      const double np_old = pp[ip], mv_old = pp[iv];
+      const double np_new = fma(ms.std_pos[i], e, xn[ip]);
+      const double nv_old = nv[(size_t)m * ms.n_pos + i];
+      const double nv_new = (np_new - np_old) / ms.T;
+      const double mv_new = (ms.b0 * nv_new + ms.b1 * nv_old - ms.a1 * mv_old) / ms.a0;
+      nv[(size_t)m * ms.n_pos + i] = nv_new;
+      pn[ip] = np_new;
+      pn[iv] = mv_new;
     }
   }
 }
@@ -622,6 +762,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   if (int e = carve(r, w)) return e;
   const int M = r->M, H = r->H, Ds = r->model.Ds, Du = r->model.Du, E = r->model.E, D = r->model.D;
   const bool meas = r->meas.enabled != 0;
+  const int Mg = r->M_global > 0 ? r->M_global : M;
   // fan the per-output chains out over side streams when one chain cannot fill the GPU and every output gets a full-M scratch
   int nmax = 1;
   for (int e = 0; e < E; e++) nmax = r->gps[e].N > nmax ? r->gps[e].N : nmax;
@@ -637,9 +778,9 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   for (int t = 0; t < H; t++) {
     const double* x_t = r->states + (size_t)t * M * Ds;
     const double* p_t = meas ? r->pol_in + (size_t)t * M * Ds : x_t;
-    policy_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(r->policy, r->model, r->noise, M, t, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
-                                                  t < H - 1 ? w.Xs : nullptr);
-    MCP_LAUNCH_CHECK();
+    if (int err = launch_policy(r->policy, r->model, r->noise, M, Mg, t, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
+                                t < H - 1 ? w.Xs : nullptr, st))
+      return err;
     if (t == H - 1) break;
     if (fan != nullptr) {
       // small problem: the E per-output chains (K* tile -> contraction -> reduce) are independent; run them side by side
@@ -662,10 +803,16 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
           return err;
       }
     }
-    integrate_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->model, r->meas, r->noise, M, t, x_t, w.mean, w.var, w.jmean, w.jvar,
-                                                   r->states + (size_t)(t + 1) * M * Ds,
-                                                   r->need_grad ? r->jac + (size_t)t * M * E * D : nullptr, p_t,
-                                                   meas ? r->pol_in + (size_t)(t + 1) * M * Ds : nullptr, w.nv);
+    if (M <= 4096)
+      integrate_warp_kernel<<<cdiv(M, 8), 256, 0, st>>>(r->model, r->meas, r->noise, M, t, x_t, w.mean, w.var, w.jmean, w.jvar,
+                                                        r->states + (size_t)(t + 1) * M * Ds,
+                                                        r->need_grad ? r->jac + (size_t)t * M * E * D : nullptr, p_t,
+                                                        meas ? r->pol_in + (size_t)(t + 1) * M * Ds : nullptr, w.nv);
+    else
+      integrate_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->model, r->meas, r->noise, M, t, x_t, w.mean, w.var, w.jmean, w.jvar,
+                                                     r->states + (size_t)(t + 1) * M * Ds,
+                                                     r->need_grad ? r->jac + (size_t)t * M * E * D : nullptr, p_t,
+                                                     meas ? r->pol_in + (size_t)(t + 1) * M * Ds : nullptr, w.nv);
     MCP_LAUNCH_CHECK();
   }
   if (r->cost.kind != 0) {
@@ -726,9 +873,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_policy_forward(con
   nz.seed = seed;
   nz.particle_offset = particle_offset;
   nz.p_dropout = p_dropout;
-  policy_fwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(p, mdl, nz, M, t, 0, x, x, u, nullptr);
-  MCP_LAUNCH_CHECK();
-  return MCP_OK;
+  return launch_policy(p, mdl, nz, M, M, t, 0, x, x, u, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_init_particles(int kind, const double* a, const double* b, int n_modes, int M, int Ds,

@@ -56,7 +56,7 @@ class Noise(C.Structure):
 
 
 class Rollout(C.Structure):
-    _fields_ = [("M", C.c_int32), ("H", C.c_int32), ("need_grad", C.c_int32), ("_pad", C.c_int32), ("model", Model),
+    _fields_ = [("M", C.c_int32), ("H", C.c_int32), ("need_grad", C.c_int32), ("M_global", C.c_int32), ("model", Model),
                 ("policy", Policy), ("cost", Cost), ("meas", Meas), ("noise", Noise), ("gps", C.POINTER(Gp)),
                 ("x0", C.c_void_p), ("states", C.c_void_p), ("inputs", C.c_void_p), ("jac", C.c_void_p),
                 ("pol_in", C.c_void_p), ("costs", C.c_void_p), ("cost_out", C.c_void_p), ("cost_stats", C.c_void_p),

@@ -197,7 +197,7 @@ class RolloutPlan:
     """Everything one rollout needs, flattened: owns the McpRollout struct and keeps every tensor it points to alive."""
 
     def __init__(self, model, gps, policy, pol_tensors, cost=None, cost_traj=None, meas=None, M=1, H=1, p_dropout=0.0,
-                 seed=0, particle_offset=0, need_grad=False, eps=None, masks=None, meas_eps=None, device=None):
+                 seed=0, particle_offset=0, need_grad=False, eps=None, masks=None, meas_eps=None, device=None, M_global=0):
         self.dev = device or gps[0].Xtr.device
         self.L = _enter(self.dev)
         self.gps = list(gps)
@@ -237,7 +237,7 @@ class RolloutPlan:
         self.ws = _workspace(dev, wsb, "rollout")
         self.gp_arr = _gp_array(self.gps)
         r = N.Rollout()
-        r.M, r.H, r.need_grad = self.M, self.H, 1 if need_grad else 0
+        r.M, r.H, r.need_grad, r.M_global = self.M, self.H, 1 if need_grad else 0, int(M_global)
         r.model, r.policy, r.cost, r.meas = model, policy, self.cost, self.meas
         r.noise.seed, r.noise.particle_offset, r.noise.p_dropout = int(seed), int(particle_offset), float(p_dropout)
         r.noise.eps = self.eps.data_ptr() if self.eps is not None else None

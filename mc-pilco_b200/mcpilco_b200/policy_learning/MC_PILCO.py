@@ -160,7 +160,7 @@ class MC_PILCO(torch.nn.Module):
         plan = ops.RolloutPlan(ml.rollout_model_struct(Ds, Du), ml.fitted_gps(), pol.policy_struct(), pol.policy_tensors(), cost=cst,
                                cost_traj=ctraj, meas=self._meas_struct(), M=count, H=H, p_dropout=p_dropout, seed=seed,
                                particle_offset=offset, need_grad=need_grad, eps=nz.get("eps"), masks=nz.get("masks"),
-                               meas_eps=nz.get("meas_eps"), device=x0.device)
+                               meas_eps=nz.get("meas_eps"), device=x0.device, M_global=int(num_particles))
         states, inputs, cost, std = _ParticleRollout.apply(plan, x0, (rank, world, group, int(num_particles)), *params)
         if fused is not None:
             key = self._trial_index if getattr(self.cost_function, "flg_var_lengthscales", False) else None

@@ -100,4 +100,28 @@ def scenario(name, seed=0):
     return sc
 
 
+def ur5_full(N=96, M=24, H=6, nb=40, seed=0):
+    """Config 4 at its TRUE dimensions (Ds = 12, Du = 6, E = 6 outputs, D = 24 gp inputs, SE + linear kernel, trajectory policy and
+    cost; test_mcpilco_ur5_mujoco.py:57-162) with small N / M / H.  No golden file: checked against the CPU oracle."""
+    rs = np.random.RandomState(2000 + seed)
+    q = rs.uniform(-1.5, 1.5, (N, 6)); dq = rs.uniform(-2, 2, (N, 6)); u = rs.uniform(-1, 1, (N, 6))
+    X = np.concatenate([dq, np.sin(q), np.cos(q), u], 1)
+    Y = 0.02 * (3 * u - 2 * np.sin(q) - 0.3 * dq) + 0.005 * rs.randn(N, 6)
+    gps = [{"log_ls": np.log(3.0) + 0.1 * rs.randn(24), "lambda": 1.0, "sigma_n": 0.05, "mean": 0.0, "mpk": [0.1 * np.exp(0.1 * rs.randn(25))]}
+           for _ in range(6)]
+    tt = np.linspace(0, 1, H)[:, None]
+    traj = np.concatenate([0.3 * np.sin(2 * tt + np.arange(6)[None] * 0.3), 0.1 * np.cos(2 * tt + np.arange(6)[None] * 0.3)], 1)
+    sc = dict(name="ur5", D=24, Ds=12, Du=6, E=6, N=N, M=M, H=H, X=X, Y=Y, gps=gps,
+              model={"kind": "speed", "use_trig": True, "angle": list(range(6)), "not_angle": list(range(6, 12)), "vel": list(range(6, 12)),
+                     "pos": list(range(6)), "T": 0.02},
+              policy={"kind": "target", "nb": nb, "centers": np.concatenate([np.pi / 2 * 2 * (rs.rand(nb, 12) - 0.5), 0.1 * 2 * (rs.rand(nb, 12) - 0.5)], 1),
+                      "lengthscales": np.pi * np.ones(24), "weight": 2 * (rs.rand(6, nb) - 0.5), "u_max": [1.0] * 6, "target_traj": traj,
+                      "bias": None, "scale": None},
+              p_dropout=0.25, cost={"kind": "sat_traj", "target_traj": traj, "ls": np.array([0.5] * 6 + [1.0] * 6)},
+              x0_mean=traj[0].copy(), x0_var=1e-6 * np.ones(12))
+    sc["eps0"] = rs.randn(M, 12); sc["eps"] = rs.randn(H - 1, M, 6)
+    sc["masks"] = (rs.rand(H, M, nb) >= 0.25).astype(np.float64)
+    return sc
+
+
 ALL = ("c1", "c2", "c3", "c4", "delta")

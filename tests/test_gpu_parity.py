@@ -204,7 +204,7 @@ def test_philox_rollout_statistics(nh):
     sh = dict(sc); sh["M"] = half
     parts = []
     for r in range(2):
-        plan, _ = nh.native_plan(sh, gps, need_grad=False, inject=False, seed=1, particle_offset=r * half)
+        plan, _ = nh.native_plan(sh, gps, need_grad=False, inject=False, seed=1, particle_offset=r * half, M_global=sc["M"])
         s, _ = plan.forward(x0[r * half:(r + 1) * half])
         parts.append(s.clone())
     assert torch.equal(torch.cat(parts, 1), outs[0][0])
@@ -328,10 +328,36 @@ def test_cost_stats_output_and_shard_merge(nh):
     for r in range(3):
         off, cnt = D.shard(sc["M"], r, 3)
         sh = dict(sc); sh["M"] = cnt
-        plan, _ = nh.native_plan(sh, gps, need_grad=False, inject=False, seed=5, particle_offset=off)
+        plan, _ = nh.native_plan(sh, gps, need_grad=False, inject=False, seed=5, particle_offset=off, M_global=sc["M"])
         plan.forward(x0[off:off + cnt])
         stats.append(plan.cost_stats.clone()); counts.append(cnt)
     mean, m2 = D.merge_cost_stats(torch.stack(stats), counts)
     cost, std = D.expected_cost_from_stats(mean, m2, sc["M"])
     close(cost, float(full.cost_out[0]), 1e-13)
     close(std, float(full.cost_out[1]), 1e-10)
+
+
+def test_ur5_true_dimensions_vs_oracle(nh):
+    """Config 4 at its real dimensions (D = 24, E = 6, Ds = 12, Du = 6): trajectories, cost and policy gradients against the CPU oracle
+    (own precompute on both sides), plus the single-step posterior and its Jacobians."""
+    from mcpilco_b200 import _ops as ops
+    sc = scenarios.ur5_full()
+    ref = Hh.oracle_rollout(sc)
+    gps = nh.native_fit(sc)
+    plan, _ = nh.native_plan(sc, gps, need_grad=True)
+    states, inputs = plan.forward(nh.x0_of(sc))
+    assert relmax(states, ref["states"]) < REL_VAL and relmax(inputs, ref["inputs"]) < REL_VAL
+    close(plan.cost_out[0], ref["cost"], REL_VAL)
+    gr = plan.backward(grad_cost=1.0)
+    for k in ("log_ls", "centers", "W"):
+        assert relmax(gr[k], ref["g_" + k]) < REL_GRAD, k
+    # posterior Jacobians of every output at D = 24 against oracle autograd
+    ogps = Hh.oracle_fit(sc)
+    Xs = sc["X"][:7] + 0.05
+    _, _, jm, jv = ops.gp_predict(gps, nh.G(Xs), jac=True)
+    for e, (sp, X, alpha, Kinv) in enumerate(ogps):
+        xs = Hh.T(Xs).requires_grad_(True)
+        mu, var = O.gp_predict(sp, X, alpha, Kinv, xs)
+        gm, = torch.autograd.grad(mu.sum(), xs, retain_graph=True)
+        gv, = torch.autograd.grad(var.sum(), xs)
+        assert relmax(jm[:, e, :], gm.numpy()) < 1e-6 and relmax(jv[:, e, :], gv.numpy()) < 1e-5
