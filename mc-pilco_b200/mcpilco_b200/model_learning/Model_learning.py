@@ -150,7 +150,8 @@ class Model_learning(torch.nn.Module):
     # ---- what the fused rollout consumes -----------------------------------------------------------------------------
     def fitted_gps(self):
         """[ops.FittedGp] for all outputs; rebuilt when pretrain_gp ran or a list entry was replaced (load_model_from_log)."""
-        key = tuple((id(a), id(k), id(x), float(n)) for a, k, x, n in zip(self.alpha_list, self.K_X_inv_list, self.gp_inputs_tr_list, self.norm_list))
+        key = tuple((id(a), id(k), id(x), float(n), tuple(p._version for p in gp.parameters()))
+                    for a, k, x, n, gp in zip(self.alpha_list, self.K_X_inv_list, self.gp_inputs_tr_list, self.norm_list, self.gp_list))
         if self._fitted_cache is None or self._fitted_cache[0] != key:
             gps = []
             for i in range(self.num_gp):

@@ -29,6 +29,11 @@ class _ParticleRollout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, x0, shard, *params):
         states, inputs = plan.forward(x0)
+        # the node keeps the trajectories alive for the backward kernel through autograd's saved-output mechanism; the plan drops its
+        # own references so that  states -> fused-cost attribute -> cost -> this node -> plan -> states  is not a reference cycle
+        # (a cycle would keep every rollout's buffers alive until Python's cyclic GC runs)
+        ctx.save_for_backward(states, inputs)
+        plan.states = plan.inputs = None
         ctx.plan, ctx.shard = plan, shard
         ctx.want_gx0 = bool(x0.requires_grad)
         ctx.n_params = len(params)
