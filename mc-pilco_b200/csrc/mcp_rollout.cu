@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
   __shared__ double s_lam[MCP_MAX_DS], s_lnext[MCP_MAX_DS], s_la[MCP_MAX_DU], s_gbias[MCP_MAX_DU];
   __shared__ double s_lnv[MCP_MAX_E], s_lmv[MCP_MAX_E], s_lnp[MCP_MAX_E];
   __shared__ double s_red[16][MCP_MAX_DP];
+  __shared__ double s_x[MCP_MAX_DS], s_px[MCP_MAX_DS], s_gs[MCP_MAX_DS], s_u[MCP_MAX_DU], s_gi[MCP_MAX_DU], s_J[MCP_MAX_E * MCP_MAX_D];
   __shared__ int s_active;
 
   if (tid < Dp) { s_il[tid] = exp(-pol.log_ls[tid]); s_glz[tid] = 0.0; }
@@ -459,17 +460,34 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
       for (int i = 0; i < MCP_MAX_E; i++) s_lnv[i] = s_lmv[i] = s_lnp[i] = 0.0;
     }
     for (int t = H - 1; t >= 0; t--) {
-      const double* x = r.states + ((size_t)t * M + m) * Ds;
-      const double* px = polin + ((size_t)t * M + m) * Ds;
-      const double* u = r.inputs + ((size_t)t * M + m) * Du;
+      // ---- stage 0: this step's checkpoint (x_t, policy input, u_t, Jacobian rows, upstream gradients) into shared memory with
+      //      one parallel, coalesced load instead of a chain of dependent scalar loads by the serial thread ----
+      {
+        const size_t row = (size_t)t * M + m;
+        if (tid < Ds) {
+          s_x[tid] = r.states[row * Ds + tid];
+          s_px[tid] = polin[row * Ds + tid];
+          s_gs[tid] = g.grad_states ? g.grad_states[row * Ds + tid] : 0.0;
+        }
+        if (tid < Du) {
+          s_u[tid] = r.inputs[row * Du + tid];
+          s_gi[tid] = g.grad_inputs ? g.grad_inputs[row * Du + tid] : 0.0;
+        }
+        if (t < H - 1)
+          for (int i = tid; i < E * D; i += blockDim.x) s_J[i] = r.jac[row * E * D + i];
+      }
+      __syncthreads();
+      const double* x = s_x;
+      const double* px = s_px;
+      const double* u = s_u;
       // ---- stage A: adjoint of x_t from cost and from the model step t -> t+1; adjoint of u_t ----
       if (tid == 0) {
         double lam[MCP_MAX_DS], lu[MCP_MAX_DU];
-        for (int j = 0; j < Ds; j++) lam[j] = g.grad_states ? g.grad_states[((size_t)t * M + m) * Ds + j] : 0.0;
-        for (int k = 0; k < Du; k++) lu[k] = g.grad_inputs ? g.grad_inputs[((size_t)t * M + m) * Du + k] : 0.0;
+        for (int j = 0; j < Ds; j++) lam[j] = s_gs[j];
+        for (int k = 0; k < Du; k++) lu[k] = s_gi[k];
         if (cost_w != 0.0) cost_grad_add(r.cost, x, t, Ds, cost_w, lam);
         if (t < H - 1) {
-          const double* J = r.jac + ((size_t)t * M + m) * E * D;
+          const double* J = s_J;
           double lx[MCP_MAX_D];
           for (int d = 0; d < D; d++) lx[d] = 0.0;
           for (int e = 0; e < E; e++) {
@@ -678,7 +696,7 @@ static int bwd_grid(int M) {
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int g = sms * 2;
+  int g = sms * 4;  // 4 resident CTAs per SM hide the latency of the per-step dependency chain
   return M < g ? M : g;
 }
 
