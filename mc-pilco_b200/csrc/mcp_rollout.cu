@@ -3,76 +3,16 @@
 // model_learning/Model_learning.py:210-229,670-718 (get_next_state), policy_learning/Policy.py:242-265,
 // 323-335,389-403 (policies), policy_learning/Cost_function.py:25-36,53-182 (costs), and the autograd
 // pass of MC_PILCO.py:522 which mcpilco_rollout_bwd replaces.
-#include "mcp_common.cuh"
+#include "mcp_rollout_dev.cuh"
 
 namespace mcp {
 
 int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, double* mean, double* var, double* jmean,
                        double* jvar, double* scratch, size_t scratch_doubles, cudaStream_t st);
-
-// ------------------------------------------------------------------------------------------------
-// small device helpers shared by forward and backward
-// ------------------------------------------------------------------------------------------------
-// policy feature j of the state seen by the policy (already divided by scale_factor)
-__device__ __forceinline__ double policy_feature(const McpPolicy& p, const double* __restrict__ x, int t, int j) {
-  double f;
-  if (p.kind == 1) {
-    if (j < p.n_na) f = x[p.na_idx[j]];
-    else if (j < p.n_na + p.n_a) f = cos(x[p.a_idx[j - p.n_na]]);
-    else f = sin(x[p.a_idx[j - p.n_na - p.n_a]]);
-  } else if (p.kind == 2) {
-    f = (j < p.Ds) ? x[j] : (p.target_traj[(size_t)t * p.Ds + (j - p.Ds)] - x[j - p.Ds]);
-  } else {
-    f = x[j];
-  }
-  return f * p.inv_scale[j];
-}
-
-__device__ __forceinline__ bool dropout_active(const McpPolicy& p, const McpNoise& nz) { return p.use_drop && nz.p_dropout > 0.0; }
-
-// tm addresses the injected mask tensor, t the Philox counter (they differ only for the stand-alone policy call)
-__device__ __forceinline__ bool keep_unit(const McpNoise& nz, int M, int nb, int tm, int t, int m, int b) {
-  if (nz.masks) return nz.masks[((size_t)tm * M + m) * nb + b] != 0;
-  return rng_keep(nz.seed, nz.particle_offset + (uint64_t)m, t, b, nz.p_dropout);
-}
-
-__device__ __forceinline__ double cost_value(const McpCost& c, const double* __restrict__ x, int t, int Ds) {
-  if (c.kind == 1) {
-    double a = (fabs(x[c.idx[0]]) - c.target[0]) * c.inv_ls[0], b = (x[c.idx[1]] - c.target[1]) * c.inv_ls[1];
-    return 1.0 - exp(-(a * a) - b * b);
-  }
-  double d = 0.0;
-  for (int i = 0; i < c.n_idx; i++) {
-    double tg = (c.kind == 2) ? c.target_traj[(size_t)t * Ds + c.idx[i]] : c.target[i];
-    double r = (x[c.idx[i]] - tg) * c.inv_ls[i];
-    d = fma(r, r, d);
-  }
-  return (c.kind == 4) ? d : 1.0 - exp(-d);
-}
-
-// lam[j] += w * d cost / d x_j
-__device__ __forceinline__ void cost_grad_add(const McpCost& c, const double* __restrict__ x, int t, int Ds, double w, double* lam) {
-  if (c.kind == 1) {
-    double th = x[c.idx[0]];
-    double a = (fabs(th) - c.target[0]) * c.inv_ls[0], b = (x[c.idx[1]] - c.target[1]) * c.inv_ls[1];
-    double e = exp(-(a * a) - b * b);
-    double sg = (th > 0.0) ? 1.0 : ((th < 0.0) ? -1.0 : 0.0);
-    lam[c.idx[0]] += w * e * 2.0 * a * c.inv_ls[0] * sg;
-    lam[c.idx[1]] += w * e * 2.0 * b * c.inv_ls[1];
-    return;
-  }
-  double d = 0.0;
-  for (int i = 0; i < c.n_idx; i++) {
-    double tg = (c.kind == 2) ? c.target_traj[(size_t)t * Ds + c.idx[i]] : c.target[i];
-    double r = (x[c.idx[i]] - tg) * c.inv_ls[i];
-    d = fma(r, r, d);
-  }
-  double e = (c.kind == 4) ? 1.0 : exp(-d);
-  for (int i = 0; i < c.n_idx; i++) {
-    double tg = (c.kind == 2) ? c.target_traj[(size_t)t * Ds + c.idx[i]] : c.target[i];
-    lam[c.idx[i]] += w * e * 2.0 * (x[c.idx[i]] - tg) * c.inv_ls[i] * c.inv_ls[i];
-  }
-}
+// fused two-launches-per-step forward for small rollouts (mcp_small.cu)
+bool small_path_ok(const McpRollout* r);
+size_t small_path_doubles(int M, int E, int Nmax);
+int rollout_fwd_small(const McpRollout* r, double* Xs, double* nv, double* scratch, size_t scratch_doubles, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // forward kernels
@@ -770,7 +710,7 @@ extern "C" __attribute__((visibility("default"))) size_t mcpilco_rollout_workspa
   size_t fixed = fixed_doubles(M, H, E, D, nb, Dp, Du, E, bwd_grid(M)) * sizeof(double);
   // small rollouts run their E per-output chains concurrently: one K*/V scratch per output
   const size_t copies = ((size_t)M * (size_t)(Nmax > 0 ? Nmax : 1) <= ((size_t)1 << 22)) ? (size_t)(E > 0 ? E : 1) : 1;
-  return fixed + copies * mcpilco_gp_predict_workspace_bytes(M, Nmax) + 16384;
+  return fixed + copies * mcpilco_gp_predict_workspace_bytes(M, Nmax) + 16384 + 65536;  // + device table of the fused small path
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const McpRollout* r, void* stream) {
@@ -793,7 +733,11 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
     init_nv_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->meas, M, Ds, r->x0, w.nv);
     MCP_LAUNCH_CHECK();
   }
-  for (int t = 0; t < H; t++) {
+  const bool small = small_path_ok(r) && w.scratch_doubles >= small_path_doubles(M, E, nmax);
+  if (small) {
+    if (int err = rollout_fwd_small(r, w.Xs, w.nv, w.scratch, w.scratch_doubles, st)) return err;
+  }
+  for (int t = 0; t < H && !small; t++) {
     const double* x_t = r->states + (size_t)t * M * Ds;
     const double* p_t = meas ? r->pol_in + (size_t)t * M * Ds : x_t;
     if (int err = launch_policy(r->policy, r->model, r->noise, M, Mg, t, t, p_t, x_t, r->inputs + (size_t)t * M * Du,

@@ -113,8 +113,19 @@ def _run_rollout(nh, sc, gps, fused_cost=True):
     return plan, states, inputs
 
 
+@pytest.fixture(params=["fused-small", "per-step"])
+def rollout_path(request, monkeypatch):
+    """Small rollouts take the fused two-launch-per-step kernels; MCPILCO_NO_SMALL_PATH=1 sends the same rollout through the per-step
+    kernels the large shapes use.  Both are held to the same golden vectors."""
+    if request.param == "per-step":
+        monkeypatch.setenv("MCPILCO_NO_SMALL_PATH", "1")
+    else:
+        monkeypatch.delenv("MCPILCO_NO_SMALL_PATH", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("name", scenarios.ALL)
-def test_rollout_formula(nh, name):
+def test_rollout_formula(nh, name, rollout_path):
     """Reference factors in; trajectories, cost and gradients out."""
     sc, g = scenarios.scenario(name), Hh.load_golden(name)
     plan, states, inputs = _run_rollout(nh, sc, nh.native_fit(sc, golden=g))
@@ -131,7 +142,7 @@ def test_rollout_formula(nh, name):
 
 
 @pytest.mark.parametrize("name", scenarios.ALL)
-def test_rollout_end_to_end(nh, name):
+def test_rollout_end_to_end(nh, name, rollout_path):
     """Own precompute; north-star tolerances."""
     sc, g = scenarios.scenario(name), Hh.load_golden(name)
     plan, states, inputs = _run_rollout(nh, sc, nh.native_fit(sc))
