@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const McpGpDev* __restr
 constexpr int SS_THREADS = 128;
 
 template <int DT, int NP, bool JAC>
-__global__ void __launch_bounds__(SS_THREADS) small_step_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __restrict__ gps, int t,
+__global__ void __launch_bounds__(SS_THREADS, 3) small_step_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __restrict__ gps, int t,
                                                                 double* __restrict__ Ks, const double* __restrict__ V, int ldk,
                                                                 size_t gp_stride, double* __restrict__ Xs, double* __restrict__ nv) {
   const McpModel& mdl = r.model;
@@ -177,30 +177,40 @@ __global__ void __launch_bounds__(SS_THREADS) small_step_kernel(const __grid_con
         if (tid < NV) s_sum[tid] = (s_w[0][tid] + s_w[1][tid]) + (s_w[2][tid] + s_w[3][tid]);
       }
       __syncthreads();
+      // finalise in parallel: thread 0 the mean / variance, thread j < D the j-th Jacobian entries
       if (tid == 0) {
-        double kd, dkd[DT];
-        KFn<DT>::kdiag_grad(s, x, kd, dkd);
         s_mean[e] = s.mean0 + s_sum[0];
-        s_var[e] = g.var_scale * (kd - s_sum[1]);
-        if (JAC) {
+        s_var[e] = g.var_scale * (KFn<DT>::kdiag(s, x) - s_sum[1]);
+      }
+      if (JAC && tid < DT && tid < D) {
+        const int j = tid;
+        const double xj = s_feat[j];
+        // d k(x,x) / dx_j of the Volterra terms: deg 1: 2 w1_j x_j ; deg 2: 2 x_j (w2a_j L2b(x,x) + w2b_j L2a(x,x))
+        double dkd = 0.0;
+        if (NP >= 1) dkd = 2.0 * s.poly_w2[0][0][j] * xj;
+        if (NP >= 2) {
+          double La = s.poly_w2[1][0][MCP_MAX_D], Lb = s.poly_w2[1][1][MCP_MAX_D];
 #pragma unroll
-          for (int j = 0; j < DT; j++) {
-            const double il2 = -2.0 * s.inv_ls[j] * s.inv_ls[j];
-            double ga = il2 * (x[j] * s_sum[2] - s_sum[4 + j]), gv = il2 * (x[j] * s_sum[3] - s_sum[4 + DT + j]);
-            if (NP >= 1) {
-              ga = fma(s.poly_w2[0][0][j], s_sum[4 + 2 * DT + j], ga);
-              gv = fma(s.poly_w2[0][0][j], s_sum[4 + 3 * DT + j], gv);
-            }
-            if (NP >= 2) {
-              ga = fma(s.poly_w2[1][0][j], s_sum[4 + 4 * DT + j], ga);
-              gv = fma(s.poly_w2[1][0][j], s_sum[4 + 5 * DT + j], gv);
-              ga = fma(s.poly_w2[1][1][j], s_sum[4 + 6 * DT + j], ga);
-              gv = fma(s.poly_w2[1][1][j], s_sum[4 + 7 * DT + j], gv);
-            }
-            s_jm[e][j] = ga;
-            s_jv[e][j] = g.var_scale * (dkd[j] - 2.0 * gv);
+          for (int jj = 0; jj < DT; jj++) {
+            La = fma(s.poly_w2[1][0][jj] * x[jj], x[jj], La);
+            Lb = fma(s.poly_w2[1][1][jj] * x[jj], x[jj], Lb);
           }
+          dkd = fma(2.0 * xj, s.poly_w2[1][0][j] * Lb + s.poly_w2[1][1][j] * La, dkd);
         }
+        const double il2 = -2.0 * s.inv_ls[j] * s.inv_ls[j];
+        double ga = il2 * (xj * s_sum[2] - s_sum[4 + j]), gv = il2 * (xj * s_sum[3] - s_sum[4 + DT + j]);
+        if (NP >= 1) {
+          ga = fma(s.poly_w2[0][0][j], s_sum[4 + 2 * DT + j], ga);
+          gv = fma(s.poly_w2[0][0][j], s_sum[4 + 3 * DT + j], gv);
+        }
+        if (NP >= 2) {
+          ga = fma(s.poly_w2[1][0][j], s_sum[4 + 4 * DT + j], ga);
+          gv = fma(s.poly_w2[1][0][j], s_sum[4 + 5 * DT + j], gv);
+          ga = fma(s.poly_w2[1][1][j], s_sum[4 + 6 * DT + j], ga);
+          gv = fma(s.poly_w2[1][1][j], s_sum[4 + 7 * DT + j], gv);
+        }
+        s_jm[e][j] = ga;
+        s_jv[e][j] = g.var_scale * (dkd - 2.0 * gv);
       }
       __syncthreads();
     }
