@@ -159,8 +159,22 @@ def run_scenario(R, name, save=True):
     return out
 
 
+def reinforce_traces(R):
+    """Traces of the REFERENCE's reinforce_policy control logic on scripted rollout costs (tests/reinforce_script.py)."""
+    import reinforce_script as RS
+    out = {}
+    for name in RS.SCRIPTS:
+        obj = R.MCP.MC_PILCO.__new__(R.MCP.MC_PILCO)  # no simulator / GP needed: apply_policy and cost_function are scripted
+        torch.nn.Module.__init__(obj)
+        obj.T_sampling, obj.dtype, obj.device, obj.state_dim, obj.input_dim = 0.05, torch.float64, CPU, 1, 1
+        for k, v in RS.run(obj, name).items():
+            out[f"{name}__{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "reinforce_traces.npz"), **out)
+
+
 if __name__ == "__main__":
     R = _import_reference()
     torch.set_num_threads(1)
     for nm in scenarios.ALL:
         run_scenario(R, nm)
+    reinforce_traces(R)

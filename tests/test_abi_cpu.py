@@ -98,3 +98,32 @@ def test_struct_builders_validate():
     assert (m.D, m.n_na, m.n_a, m.kind, m.use_trig) == (6, 3, 1, 1, 1)
     ms = P.meas_struct([0, 2], [1, 3], [3e-3, 3e-3], 0.5, 1 / 30)
     assert abs(ms.b0 - 0.5) < 1e-15 and abs(ms.a1) < 1e-15 and ms.enabled == 1
+
+
+def test_class_kernel_terms_match_flat_packing():
+    """The class layer describes a kernel as differentiable torch terms (GP_prior._kernel_terms); the spec derived from them must be
+    the one _pack builds from the flat dict (itself checked against the oracle above)."""
+    import mcpilco_b200.gpr_lib.GP_prior.GP_prior as GP
+    import mcpilco_b200.gpr_lib.GP_prior.Sparse_GP as SP
+    import mcpilco_b200.gpr_lib.GP_prior.Stationary_GP as SGP
+    from mcpilco_b200 import _pack as P
+    rs = np.random.RandomState(1)
+    D = 7
+    act_se, act_mpk = np.array([0, 2, 3, 5]), np.array([1, 2, 6])
+    log_ls = rs.randn(4)
+    mpk = [np.exp(rs.randn(4) - 3), np.exp(rs.randn(6) - 3)]
+    rbf = SGP.RBF(act_se, lengthscales_init=np.exp(log_ls), lambda_init=np.array([0.7]), sigma_n_init=np.array([0.2]), mean_init=np.array([-0.4]),
+                  sigma_n_num=1e-3)
+    vol = SP.get_Volterra_MPK_GP(act_mpk, 2, Sigma_pos_par_init_list=mpk, flg_train_Sigma_pos_par_list=[True, True])
+    s = GP.Sum_Independent_GP(rbf, vol).gp_spec(D)
+    ref = P.new_gp_spec(D)
+    P.add_se(ref, act_se, log_ls, np.log(0.7), -0.4)
+    P.add_mpk(ref, act_mpk, 1, True, np.log(mpk[0]))
+    P.add_mpk(ref, act_mpk, 2, False, np.log(mpk[1]))
+    assert (s.has_se, s.n_poly, list(s.poly_deg)) == (1, 2, [1, 2, 0]) and abs(s.lambda_ - 0.7) < 1e-15 and s.mean0 == -0.4
+    np.testing.assert_allclose(np.array(s.inv_ls), np.array(ref.inv_ls), rtol=1e-14)
+    np.testing.assert_allclose(np.ctypeslib.as_array(s.poly_w2), np.ctypeslib.as_array(ref.poly_w2), rtol=1e-13)
+    assert abs(s.sigma_n2 - (0.2 ** 2 + 1e-6)) < 1e-15
+    # a scalar (non-ARD) lengthscale broadcasts over the active dimensions
+    iso = SGP.RBF(np.arange(3), lengthscales_init=np.array([2.0]), sigma_n_init=np.array([0.1])).gp_spec(3)
+    assert list(iso.inv_ls)[:3] == [0.5, 0.5, 0.5]

@@ -1,0 +1,36 @@
+"""CPU: control logic of MC_PILCO.reinforce_policy against traces recorded from the REFERENCE's reinforce_policy
+(reference MC_PILCO.py:375-613) driven by the same scripted rollout costs (tests/reinforce_script.py): NaN re-sampling, policy
+re-initialisation and restart, cost-difference monitors, learning-rate halving with dropout reduction, early exit.  No GP, no CUDA:
+apply_policy / cost_function are replaced by the script on both sides."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import reinforce_script as RS
+
+GOLD = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reinforce_traces.npz")))
+
+
+def make_obj():
+    import mcpilco_b200.policy_learning.MC_PILCO as MCP
+    obj = MCP.MC_PILCO.__new__(MCP.MC_PILCO)
+    torch.nn.Module.__init__(obj)
+    obj.T_sampling, obj.dtype, obj.device, obj.state_dim, obj.input_dim = 0.05, torch.float64, torch.device("cpu"), 1, 1
+    obj._trial_index, obj._seed_base, obj._rollouts = None, None, 0
+    return obj
+
+
+@pytest.mark.parametrize("name", RS.SCRIPTS)
+def test_reinforce_policy_control_logic(name):
+    res = RS.run(make_obj(), name)
+    g = {k.split("__", 1)[1]: v for k, v in GOLD.items() if k.startswith(name + "__")}
+    assert len(res["cost_list"]) == len(g["cost_list"])                      # same number of optimisation steps (early exit included)
+    assert int(res["n_rollouts"]) == int(g["n_rollouts"])                    # same number of rollouts (NaN re-sampling included)
+    assert int(res["reinits"]) == int(g["reinits"])                          # same number of policy re-initialisations
+    np.testing.assert_array_equal(res["dropouts"], g["dropouts"])            # same p_dropout handed to every rollout
+    np.testing.assert_allclose(res["cost_list"], g["cost_list"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(res["std_list"], g["std_list"], rtol=1e-12)
+    np.testing.assert_allclose(res["w_final"], g["w_final"], rtol=1e-10)     # same optimiser trajectory (lr schedule included)
+    assert res["states"].shape == g["states"].shape
