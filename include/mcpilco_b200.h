@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 3
+#define MCP_ABI_VERSION 4
 
 #define MCP_MAX_D 32    /* gp-input dimension            */
 #define MCP_MAX_DS 16   /* state dimension               */
@@ -70,6 +70,11 @@ typedef struct McpGp {
   const double* alpha; /* [N]      */
   const double* Kinv;  /* [N, ld_kinv] symmetric */
   double var_scale;    /* norm_list[i]**2, Model_learning.py:220-221 */
+  /* OPT-IN error-compensated INT8 tensor-core contraction (mcpilco_ozaki_prepare); ozaki_slices == 0 selects the native FP64 path */
+  const int8_t* kinv_planes; /* reversed digit planes of Kinv, mcpilco_ozaki_plane_bytes(N, slices) bytes */
+  const int32_t* kinv_exp;   /* [N] row exponents */
+  int32_t ozaki_slices;      /* 0 (off), 7 (56-bit) or 8 (64-bit operands) */
+  int32_t _pad;
 } McpGp;
 
 /* ---- state -> gp-input map and integration (Model_learning.py:450-456,471-493,564-579,670-718) ---- */
@@ -247,6 +252,19 @@ int mcpilco_init_particles(int kind, const double* a, const double* b, int n_mod
  * returns the summed kernel time (ms), the number of bracketed launches and their summed flop count (2 m n k each). */
 int mcpilco_prof_enable(int on);
 int mcpilco_prof_read(double* total_ms, uint64_t* launches, double* flops);
+
+/* OPT-IN variant of the posterior contraction V = K* Kinv on the INT8 tensor cores (tcgen05) with error compensation (Ozaki scheme:
+ * `slices` balanced base-256 digit planes per operand, exact int32 plane products, fp64 recombination).  slices = 8 reproduces the
+ * fp64 contraction to ~1e-12 relative, slices = 7 to ~1e-9 (tolerances on the posterior variance: DESIGN.md).  prepare() slices one
+ * GP's Kinv once per model update into caller-owned buffers that are then referenced from McpGp.  Requires N * slices <= 65536. */
+int mcpilco_ozaki_available(void);
+size_t mcpilco_ozaki_plane_bytes(int N, int slices);
+int mcpilco_ozaki_prepare(const double* Kinv, int N, int ld, int slices, int8_t* planes, int32_t* exponents, void* stream);
+/* the contraction on its own: V[M, N] (ldv) = A[M, N] (lda) * Kinv^T from Kinv's prepared planes (used by mcpilco_gp_predict /
+ * mcpilco_rollout_fwd when McpGp.ozaki_slices != 0; exported for tests and benchmarks) */
+size_t mcpilco_ozaki_scratch_bytes(int M, int N, int slices);
+int mcpilco_ozaki_contract(const double* A, int lda, int M, int N, int slices, const int8_t* planes, const int32_t* exponents, double* V,
+                           int ldv, void* scratch, size_t scratch_bytes, void* stream);
 
 /* sizeof() of {McpGpSpec, McpGp, McpModel, McpPolicy, McpCost, McpMeas, McpNoise, McpRollout, McpRolloutGrad};
  * returns how many there are.  Lets a binding check its struct layout. */

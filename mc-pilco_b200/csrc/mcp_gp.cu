@@ -657,6 +657,11 @@ static bool wide_reduce_ok(const McpGpSpec& s) {
 
 static inline int ld16(int n) { return (n + 15) / 16 * 16; }
 
+// opt-in INT8 tensor-core contraction (mcp_ozaki.cu)
+size_t ozaki_scratch_bytes(int mc, int N, int S);
+int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t* Bplanes, const int32_t* Bexp, double* V, int ldv, void* scratch,
+                   size_t scratch_bytes, cudaStream_t st);
+
 // posterior of ONE GP for a chunk of particles through scratch [2 x Mc x ld16(N)]
 int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, double* mean, double* var, double* jmean,
                        double* jvar, double* scratch, size_t scratch_doubles, cudaStream_t st) {
@@ -664,9 +669,14 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
   MCP_CHECK_ARG(N >= 1 && g.Xtr && g.alpha && g.Kinv, "gp %d: null training data", e);
   MCP_CHECK_ARG(g.ld_kinv >= N && g.ld_kinv % 2 == 0 && ((uintptr_t)g.Kinv % 16) == 0,
                 "gp %d: Kinv must be 16-byte aligned with an even leading dimension >= N (ld=%d N=%d)", e, g.ld_kinv, N);
+  const int oz = g.ozaki_slices;
+  MCP_CHECK_ARG(oz == 0 || (g.kinv_planes && g.kinv_exp), "gp %d: ozaki_slices set without digit planes", e);
+  // doubles of scratch per particle: K* and V rows, plus (INT8 variant) digit planes, exponent and the int32 product planes
   size_t per = 2 * (size_t)ldk;
-  MCP_CHECK_ARG(scratch_doubles >= per, "posterior workspace too small for N=%d", N);
-  int Mc = (int)((scratch_doubles / per) < (size_t)M ? (scratch_doubles / per) : (size_t)M);
+  if (oz) per += (ozaki_scratch_bytes(1024, N, oz) / 1024 + 7) / 8 + 1;
+  MCP_CHECK_ARG(scratch_doubles >= per * (oz ? 64 : 1) + (oz ? 16384 : 0), "posterior workspace too small for N=%d", N);
+  const size_t usable = scratch_doubles - (oz ? 16384 : 0);
+  int Mc = (int)((usable / per) < (size_t)M ? (usable / per) : (size_t)M);
   const bool jac = jmean != nullptr && jvar != nullptr;
   for (int m0 = 0; m0 < M; m0 += Mc) {
     int mc = (M - m0 < Mc) ? (M - m0) : Mc;
@@ -675,6 +685,11 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     const double* xs = Xs + (size_t)m0 * g.spec.D;
     if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
     prof_begin(st);
+    if (oz) {
+      void* osc = (void*)(scratch + 2 * (size_t)Mc * ldk);
+      const size_t osb = (scratch_doubles - 2 * (size_t)Mc * ldk) * sizeof(double);
+      if (int err = ozaki_contract(Ks, ldk, mc, N, oz, g.kinv_planes, g.kinv_exp, V, ldk, osc, osb, st)) return err;
+    } else
     // the TMA kernel's 128 x 128 tiles need enough of them to fill the GPU; below that the small-tile cp.async kernel wins
     if ((size_t)cdiv(mc, 128) * cdiv(N, 128) >= 96 && dgemm_tma_usable(Ks, ldk, g.Kinv, g.ld_kinv, V, ldk)) {
       if (int err = dgemm_nt_tma(mc, N, N, 1.0, Ks, ldk, g.Kinv, g.ld_kinv, V, ldk, st)) return err;

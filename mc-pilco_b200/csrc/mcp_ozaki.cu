@@ -1,0 +1,188 @@
+// Error-compensated INT8 tensor-core variant of the posterior contraction  V[M,N] = A[M,K] * B[N,K]^T  (A = K*, B = K^-1) —
+// SURVEY.md §8 f4, the only route past the native FP64 pipe (37 TFLOP/s) on B200.  OPT-IN; the default path stays native fp64.
+//
+// Ozaki scheme I with exact integer slicing:
+//   * each row of A (column of the product's right factor B) is scaled by a power of two 2^e so that |a| 2^-e < 1/4, converted to a
+//     64-bit fixed-point integer F = rint(a 2^(8S - e)) and written as S balanced base-256 digits d_t in [-128, 127]
+//     (a 2^-e = sum_t d_t 256^-(t+1), exact to 2^-8S);
+//   * the product keeps the S(S+1)/2 digit-plane products with t + u < S:   A B^T = 2^(eA+eB) sum_w 256^-(w+2) C_w,
+//     C_w = sum_{t+u=w} A_t B_u^T, every C_w an EXACT int32 GEMM (|C_w| <= (w+1) K 2^14 < 2^31 for K <= 8192);
+//   * storing A's planes side by side along K and B's planes in REVERSE order makes every C_w ONE int8 GEMM with
+//     K_eff = (w+1) K over contiguous sub-ranges: S launches instead of S(S+1)/2, no read-modify-write of C;
+//   * a combine kernel sums the S int32 planes from the least significant up, in fp64, and applies the row/column scales.
+// The int8 GEMM runs on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMA-fed, int32 accumulators in TMEM — SASS:
+// UTCIMMA / UTMALDG / LDTM); it is instantiated from the CUTLASS 4.x collective templates vendored in this image (header-only),
+// the slicing, plane layout and combine kernels are hand-written.  S = 8 carries 64 bits per entry (fp64-class results), S = 7
+// carries 56.  Measured accuracy and rates: DESIGN.md §4.
+#include "mcp_common.cuh"
+
+#ifdef MCP_WITH_CUTLASS
+#include "cute/tensor.hpp"
+#include "cutlass/cutlass.h"
+#include "cutlass/epilogue/collective/collective_builder.hpp"
+#include "cutlass/gemm/collective/collective_builder.hpp"
+#include "cutlass/gemm/device/gemm_universal_adapter.h"
+#include "cutlass/gemm/kernel/gemm_universal.hpp"
+#endif
+
+namespace mcp {
+
+// ---- slicing: one warp per row -----------------------------------------------------------------------------------
+// planes[row][p][k], p = t (reverse == 0) or S-1-t (reverse == 1); row stride S * Kp bytes; columns K..Kp-1 are zero.
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ A, int rows, int K, int ld, int S, int Kp, int reverse,
+                                                          int8_t* __restrict__ planes, int32_t* __restrict__ expo) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const double* a = A + (size_t)row * ld;
+  double mx = 0.0;
+  for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(a[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int e = (mx > 0.0 && isfinite(mx)) ? ilogb(mx) + 3 : 0;  // |a| 2^-e < 1/4: the most significant balanced digit stays within
+                                                                   // [-65, 65] after the carries from below (no wrap at +128)
+  if (lane == 0) expo[row] = e;
+  int8_t* out = planes + (size_t)row * S * Kp;
+  const int sh = 8 * S - e;
+  for (int k = lane; k < Kp; k += 32) {
+    long long F = 0;
+    if (k < K) {
+      const double v = a[k];
+      F = isfinite(v) ? __double2ll_rn(scalbn(v, sh)) : 0;  // |F| < 2^(8S-2) <= 2^62
+    }
+#pragma unroll 1
+    for (int t = S - 1; t >= 0; t--) {
+      const long long d = ((F + 128) & 255) - 128;  // balanced digit in [-128, 127]
+      F = (F - d) >> 8;
+      out[(size_t)(reverse ? S - 1 - t : t) * Kp + k] = (int8_t)d;
+    }
+  }
+}
+
+// ---- combine: V = 2^(eA + eB) sum_w 256^-(w+2) C_w, least significant plane first ---------------------------------
+__global__ void __launch_bounds__(256) ozaki_combine_kernel(const int32_t* __restrict__ C, size_t plane_stride, int ldc, int M, int N, int S,
+                                                            const int32_t* __restrict__ eA, const int32_t* __restrict__ eB,
+                                                            double* __restrict__ V, int ldv) {
+  const int n = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  const int32_t* c = C + (size_t)m * ldc + n;
+  double acc = 0.0;
+  for (int w = S - 1; w >= 0; w--) acc = fma((double)c[(size_t)w * plane_stride], scalbn(1.0, -8 * (w + 2)), acc);
+  V[(size_t)m * ldv + n] = scalbn(acc, eA[m] + eB[n]);
+}
+
+#ifdef MCP_WITH_CUTLASS
+namespace {
+using namespace cute;
+using ElemAB = int8_t;
+using ElemC = int32_t;
+using TileShape_ = Shape<_128, _128, _128>;
+using ClusterShape_ = Shape<_1, _1, _1>;
+using Epi = typename cutlass::epilogue::collective::CollectiveBuilder<
+    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape_, ClusterShape_, cutlass::epilogue::collective::EpilogueTileAuto, ElemC,
+    ElemC, ElemC, cutlass::layout::RowMajor, 4, ElemC, cutlass::layout::RowMajor, 4,
+    cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
+using Main = typename cutlass::gemm::collective::CollectiveBuilder<
+    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElemAB, cutlass::layout::RowMajor, 16, ElemAB, cutlass::layout::ColumnMajor, 16, ElemC,
+    TileShape_, ClusterShape_, cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename Epi::SharedStorage))>,
+    cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
+using GemmKernel_ = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, Main, Epi, void>;
+using Gemm_ = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel_>;
+}  // namespace
+
+// C[M,N] (int32, ldc) = A[M,K] (int8, lda) * B[N,K]^T (int8, ldb)
+static int int8_gemm(const int8_t* A, int lda, const int8_t* B, int ldb, int32_t* C, int ldc, int M, int N, int K, void* ws, size_t wsb,
+                     cudaStream_t st) {
+  using SA = typename Gemm_::GemmKernel::StrideA;
+  using SB = typename Gemm_::GemmKernel::StrideB;
+  using SC = typename Gemm_::GemmKernel::StrideC;
+  SA sa = make_stride(int64_t(lda), Int<1>{}, int64_t(0));
+  SB sb = make_stride(int64_t(ldb), Int<1>{}, int64_t(0));
+  SC sc = make_stride(int64_t(ldc), Int<1>{}, int64_t(0));
+  typename Gemm_::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}, {A, sa, B, sb}, {{1, 0}, C, sc, C, sc}};
+  Gemm_ gemm;
+  MCP_CHECK_ARG(gemm.can_implement(args) == cutlass::Status::kSuccess, "ozaki: int8 GEMM %dx%dx%d (lda %d ldb %d ldc %d) not implementable", M, N,
+                K, lda, ldb, ldc);
+  MCP_CHECK_ARG(Gemm_::get_workspace_size(args) <= wsb, "ozaki: int8 GEMM workspace too small");
+  if (gemm.initialize(args, ws, st) != cutlass::Status::kSuccess || gemm.run(st) != cutlass::Status::kSuccess) {
+    set_error("ozaki: int8 GEMM launch failed");
+    return MCP_E_CUDA;
+  }
+  count_launch();
+  return MCP_OK;
+}
+#endif
+
+int ozaki_kp(int K) { return (K + 127) / 128 * 128; }
+
+// bytes of the digit planes of a [rows x K] matrix with S slices
+size_t ozaki_plane_bytes(int rows, int K, int S) { return (size_t)rows * S * ozaki_kp(K); }
+
+// scratch for one contraction of mc particles against N points: A planes + A exponents + S int32 planes + gemm workspace
+size_t ozaki_scratch_bytes(int mc, int N, int S) {
+  return align_up(ozaki_plane_bytes(mc, N, S), 256) + align_up((size_t)mc * 4, 256) + (size_t)S * mc * align_up((size_t)N, 4) * 4 + 65536 + 1024;
+}
+
+int ozaki_slice(const double* A, int rows, int K, int ld, int S, int reverse, int8_t* planes, int32_t* expo, cudaStream_t st) {
+  MCP_CHECK_ARG(S >= 2 && S <= 8, "ozaki: slices %d outside [2, 8]", S);
+  MCP_CHECK_ARG((long long)S * K <= (1ll << 16), "ozaki: S * K = %lld exceeds 65536 (int32 accumulation bound)", (long long)S * K);
+  if (rows <= 0) return MCP_OK;
+  ozaki_slice_kernel<<<cdiv(rows, 8), 256, 0, st>>>(A, rows, K, ld, S, ozaki_kp(K), reverse, planes, expo);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+// V[mc, N] (fp64, ldv) = A[mc, N] (fp64, lda) * Binv^T given B's reversed digit planes / exponents
+int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t* Bplanes, const int32_t* Bexp, double* V, int ldv, void* scratch,
+                   size_t scratch_bytes, cudaStream_t st) {
+#ifdef MCP_WITH_CUTLASS
+  MCP_CHECK_ARG(scratch_bytes >= ozaki_scratch_bytes(mc, N, S), "ozaki: scratch too small");
+  const int Kp = ozaki_kp(N), ldc = (int)align_up((size_t)N, 4);
+  char* p = (char*)align_up((size_t)scratch, 256);
+  int8_t* Ap = (int8_t*)p; p += align_up(ozaki_plane_bytes(mc, N, S), 256);
+  int32_t* Ae = (int32_t*)p; p += align_up((size_t)mc * 4, 256);
+  int32_t* C = (int32_t*)p; p += (size_t)S * mc * ldc * 4;
+  void* gws = (void*)align_up((size_t)p, 256);
+  const size_t plane_stride = (size_t)mc * ldc;
+  if (int e = ozaki_slice(A, mc, N, lda, S, 0, Ap, Ae, st)) return e;
+  for (int w = 0; w < S; w++) {
+    // C_w = [A_0 .. A_w] * [B_w .. B_0]^T : A planes 0..w are the first (w+1) Kp columns; reversed B planes S-1-w .. S-1 the last ones
+    if (int e = int8_gemm(Ap, S * Kp, Bplanes + (size_t)(S - 1 - w) * Kp, S * Kp, C + w * plane_stride, ldc, mc, N, (w + 1) * Kp, gws, 65536, st))
+      return e;
+  }
+  ozaki_combine_kernel<<<dim3(cdiv(N, 256), mc), 256, 0, st>>>(C, plane_stride, ldc, mc, N, S, Ae, Bexp, V, ldv);
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+#else
+  set_error("ozaki: this build has no CUTLASS headers (MCP_WITH_CUTLASS undefined)");
+  return MCP_E_ARG;
+#endif
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_ozaki_available(void) {
+#ifdef MCP_WITH_CUTLASS
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" __attribute__((visibility("default"))) size_t mcpilco_ozaki_plane_bytes(int N, int slices) { return ozaki_plane_bytes(N, N, slices); }
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_ozaki_prepare(const double* Kinv, int N, int ld, int slices, int8_t* planes,
+                                                                             int32_t* exponents, void* stream) {
+  MCP_CHECK_ARG(Kinv && planes && exponents && N >= 1 && ld >= N, "ozaki_prepare: bad arguments");
+  return ozaki_slice(Kinv, N, N, ld, slices, 1, planes, exponents, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) size_t mcpilco_ozaki_scratch_bytes(int M, int N, int slices) { return ozaki_scratch_bytes(M, N, slices); }
+
+extern "C" __attribute__((visibility("default"))) int mcpilco_ozaki_contract(const double* A, int lda, int M, int N, int slices, const int8_t* planes,
+                                                                              const int32_t* exponents, double* V, int ldv, void* scratch,
+                                                                              size_t scratch_bytes, void* stream) {
+  MCP_CHECK_ARG(A && planes && exponents && V && scratch && M >= 1 && N >= 1 && lda >= N && ldv >= N, "ozaki_contract: bad arguments");
+  return ozaki_contract(A, lda, M, N, slices, planes, exponents, V, ldv, scratch, scratch_bytes, (cudaStream_t)stream);
+}

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 MAX_D, MAX_DS, MAX_DU, MAX_E, MAX_DP, MAX_POLY, MAX_DEG = 32, 16, 8, 16, 32, 3, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcpilco_b200.so")
 
@@ -21,7 +21,8 @@ class GpSpec(C.Structure):
 
 class Gp(C.Structure):
     _fields_ = [("spec", GpSpec), ("N", C.c_int32), ("ld_kinv", C.c_int32), ("Xtr", C.c_void_p), ("alpha", C.c_void_p),
-                ("Kinv", C.c_void_p), ("var_scale", C.c_double)]
+                ("Kinv", C.c_void_p), ("var_scale", C.c_double), ("kinv_planes", C.c_void_p), ("kinv_exp", C.c_void_p),
+                ("ozaki_slices", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Model(C.Structure):
@@ -92,6 +93,12 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p]),
     "mcpilco_init_particles": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
                                          C.c_void_p]),
+    "mcpilco_ozaki_available": (C.c_int, []),
+    "mcpilco_ozaki_plane_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mcpilco_ozaki_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcpilco_ozaki_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "mcpilco_ozaki_contract": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]),
     "mcpilco_prof_enable": (C.c_int, [C.c_int]),
     "mcpilco_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "mcpilco_launch_count": (C.c_uint64, [C.c_int]),

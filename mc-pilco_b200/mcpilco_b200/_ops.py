@@ -136,7 +136,9 @@ def kinv_for_kernels(Kinv):
 class FittedGp:
     """One output's fitted GP: what Model_learning keeps per gp_index (Model_learning.py:172-175)."""
 
-    def __init__(self, spec, Xtr, alpha, Kinv, var_scale=1.0):
+    def __init__(self, spec, Xtr, alpha, Kinv, var_scale=1.0, ozaki_slices=None):
+        """ozaki_slices: None -> environment MCPILCO_OZAKI (default 0 = native FP64 contraction); 7 or 8 -> the opt-in INT8
+        tensor-core contraction with error compensation (include/mcpilco_b200.h, mcpilco_ozaki_prepare)."""
         self.spec = spec
         self.Xtr = _c(Xtr, "gp_inputs")
         self.alpha = _c(alpha, "alpha").reshape(-1)
@@ -145,12 +147,28 @@ class FittedGp:
         self.N = self.Xtr.shape[0]
         if self.Xtr.shape[1] != spec.D or self.alpha.numel() != self.N or self.Kinv.shape[0] != self.N:
             raise RuntimeError("FittedGp: inconsistent shapes")
+        import os
+        self.ozaki = int(os.environ.get("MCPILCO_OZAKI", "0")) if ozaki_slices is None else int(ozaki_slices)
+        self.planes = self.plane_exp = None
+        if self.ozaki:
+            L = _enter(self.Xtr.device)
+            if not L.mcpilco_ozaki_available():
+                raise RuntimeError("mcpilco_b200: the INT8 (Ozaki) contraction was requested but this build has no CUTLASS headers")
+            if self.ozaki not in (7, 8) or self.N * self.ozaki > 65536:
+                raise RuntimeError("mcpilco_b200: ozaki_slices must be 7 or 8 with N * slices <= 65536 (N = %d)" % self.N)
+            self.planes = torch.empty(L.mcpilco_ozaki_plane_bytes(self.N, self.ozaki), dtype=torch.uint8, device=self.Xtr.device)
+            self.plane_exp = torch.empty(self.N, dtype=torch.int32, device=self.Xtr.device)
+            N.check(L.mcpilco_ozaki_prepare(_ptr(self.Kinv), self.N, self.ld, self.ozaki, _ptr(self.planes), _ptr(self.plane_exp),
+                                            _stream(self.Xtr.device)))
 
     def fill(self, g):
         C.memmove(C.byref(g.spec), C.byref(self.spec), C.sizeof(N.GpSpec))
         g.N, g.ld_kinv = self.N, self.ld
         g.Xtr, g.alpha, g.Kinv = self.Xtr.data_ptr(), self.alpha.data_ptr(), self.Kinv.data_ptr()
         g.var_scale = self.var_scale
+        g.ozaki_slices = self.ozaki
+        g.kinv_planes = self.planes.data_ptr() if self.planes is not None else None
+        g.kinv_exp = self.plane_exp.data_ptr() if self.plane_exp is not None else None
 
 
 def _gp_array(gps):
@@ -342,3 +360,19 @@ def prof_read():
     ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
     N.check(N.lib().mcpilco_prof_read(C.byref(ms), C.byref(n), C.byref(fl)))
     return ms.value, int(n.value), fl.value
+
+
+def ozaki_matmul(A, B, slices=8):
+    """A [M, N] @ B[N, N]^T through the INT8 tensor-core contraction (test / benchmark hook)."""
+    A, B = _c(A, "A"), _c(B, "B")
+    L = _enter(A.device)
+    M, Nn = A.shape
+    planes = torch.empty(L.mcpilco_ozaki_plane_bytes(Nn, slices), dtype=torch.uint8, device=A.device)
+    pexp = torch.empty(Nn, dtype=torch.int32, device=A.device)
+    N.check(L.mcpilco_ozaki_prepare(_ptr(B), Nn, B.stride(0), slices, _ptr(planes), _ptr(pexp), _stream(A.device)))
+    V = torch.empty(M, Nn, dtype=F64, device=A.device)
+    sb = L.mcpilco_ozaki_scratch_bytes(M, Nn, slices)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=A.device)
+    N.check(L.mcpilco_ozaki_contract(_ptr(A), A.stride(0), M, Nn, slices, _ptr(planes), _ptr(pexp), _ptr(V), Nn, _ptr(scratch), sb,
+                                     _stream(A.device)))
+    return V, planes, pexp
