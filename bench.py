@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--cpu-horizon", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
+    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 7, 8],
+                    help="opt-in INT8 tensor-core contraction with error compensation for the main measurement (default 0: native fp64)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra timing of the opt-in INT8 contraction variants")
     ap.add_argument("--se-only", action="store_true", help="config 2 kernel (pure squared-exponential)")
     return ap.parse_args()
 
@@ -217,6 +220,7 @@ def own_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     sc = W.cartpole_sweep(args.train_points, se_only=args.se_only)
+    os.environ["MCPILCO_OZAKI"] = str(args.ozaki)
     obj = build_objects(sc, dev)
     ml, pol = obj.model_learning, obj.control_policy
     torch.cuda.synchronize()
@@ -310,6 +314,33 @@ def own_arm(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = M_global * H * args.e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- opt-in variants of the dominant contraction (same workload, same API; reported beside the fp64 headline) ----
+    variants = {}
+    from mcpilco_b200 import _native as _Nn
+    if not args.no_variants and args.ozaki == 0 and _Nn.lib().mcpilco_ozaki_available() and args.train_points * 8 <= 65536:
+        for S, tol in ((8, "posterior variance within 1e-7 relative of the fp64 path (tests/test_gpu_parity.py)"),
+                       (7, "posterior variance within 1e-5 relative of the fp64 path")):
+            os.environ["MCPILCO_OZAKI"] = str(S)
+            ml._fitted_cache = None
+            step(); step()
+            barrier()
+            ops.prof_enable(True)
+            e0.record()
+            for _ in range(2):
+                vc, _ = step()
+            e1.record()
+            barrier()
+            vms = max_over_ranks(e0.elapsed_time(e1)) / 2
+            g_ms, g_n, g_fl = ops.prof_read()
+            ops.prof_enable(False)
+            variants["ozaki%d" % S] = {"value": M_global * H / (vms * 1e-3), "unit": "particle-steps/s", "ms_per_step": vms, "cost": float(vc.detach()),
+                                       "contraction": "int8 tcgen05 tensor cores, %d balanced base-256 digit planes per operand, int32 accumulation in TMEM, "
+                                                      "fp64 recombination" % S,
+                                       "contraction_tflops_fp64_equivalent": g_fl / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else None,
+                                       "tolerance": tol}
+        os.environ["MCPILCO_OZAKI"] = "0"
+        ml._fitted_cache = None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -326,18 +357,20 @@ def own_arm(args):
         except Exception:
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.ozaki == 0 else "f64 results via int8 digit planes (Ozaki-%d)" % args.ozaki, "data": "synthetic",
             "config": dict(workload_config(args, world), precompute_ms=precompute_ms, cost=cost_v, e2e_steps=args.e2e_steps,
                            flops_per_particle_step=F, step_tflops_per_gpu=F * value / world * 1e-12,
                            step_frac_of_fp64_peak=F * value / world * 1e-12 / FP64_PEAK_TFLOPS),
-            "roofline": {"bound": "tensor", "kernel": "dgemm_nt_kernel (V = K* Kinv, FP64 DMMA.8x8x4)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": ("dgemm_tma_kernel (V = K* Kinv, FP64 DMMA.8x8x4, TMA + mbarrier pipeline)" if args.ozaki == 0 else
+                                                      "int8 tcgen05 plane GEMMs + slice/combine (fp64-equivalent flops)"), "achieved": achieved,
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": None if achieved is None else achieved / FP64_PEAK_TFLOPS,
                          "traffic": traffic, "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                          "flops_per_launch": gemm_fl / max(gemm_n, 1), "kernel_share_of_step": gemm_ms / ms,
                          "peak_source": "own measurement on this pool (FP64 is absent from MEASURED_PEAKS.json): profiles/microbench/r01_fp64_peaks.txt"},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.e2e_steps},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks, "variants": variants}
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         fitted = [(g.alpha.detach().cpu().reshape(-1, 1), g.Kinv.detach().cpu().contiguous()) for g in ml.fitted_gps()]

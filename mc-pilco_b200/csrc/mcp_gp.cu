@@ -674,7 +674,7 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
   // doubles of scratch per particle: K* and V rows, plus (INT8 variant) digit planes, exponent and the int32 product planes
   size_t per = 2 * (size_t)ldk;
   if (oz) per += (ozaki_scratch_bytes(1024, N, oz) / 1024 + 7) / 8 + 1;
-  MCP_CHECK_ARG(scratch_doubles >= per * (oz ? 64 : 1) + (oz ? 16384 : 0), "posterior workspace too small for N=%d", N);
+  MCP_CHECK_ARG(scratch_doubles >= per + (oz ? 16384 : 0), "posterior workspace too small for N=%d", N);
   const size_t usable = scratch_doubles - (oz ? 16384 : 0);
   int Mc = (int)((usable / per) < (size_t)M ? (usable / per) : (size_t)M);
   const bool jac = jmean != nullptr && jvar != nullptr;
@@ -729,13 +729,21 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
 }  // namespace mcp
 
 extern "C" __attribute__((visibility("default"))) size_t mcpilco_gp_predict_workspace_bytes(int M, int Nmax) {
-  // scratch for K* and V = K* K^-1 of one particle chunk; capped at 2 GiB, at least 128 particles
-  size_t per = 2 * (size_t)mcp::ld16(Nmax > 0 ? Nmax : 1) * sizeof(double);
-  size_t want = per * (size_t)(M > 0 ? M : 1);
-  size_t cap = (size_t)2 << 30, floor_ = per * 128;
+  // scratch for K* and V = K* K^-1 of one particle chunk (plus, when the opt-in INT8 contraction is possible for this N, its digit
+  // planes and int32 product planes); capped at 2 GiB, at least 128 particles
+  const int N = Nmax > 0 ? Nmax : 1;
+  size_t per = 2 * (size_t)mcp::ld16(N) * sizeof(double);
+  size_t fixed = 256;
+  if ((long long)N * 8 <= 65536) {
+    per += mcp::ozaki_scratch_bytes(1024, N, 8) / 1024 + 8;
+    fixed += 16384 * sizeof(double);
+  }
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  size_t want = per * m;
+  const size_t cap = (size_t)2 << 30, floor_ = per * 128;
   if (want > cap) want = cap;
-  if (want < floor_) want = floor_ < per * (size_t)(M > 0 ? M : 1) ? floor_ : per * (size_t)(M > 0 ? M : 1);
-  return want + 256;
+  if (want < floor_) want = floor_ < per * m ? floor_ : per * m;
+  return want + fixed;
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_gp_predict(const McpGp* gps, int E, const double* Xs, int M, double* mean, double* var, double* jmean,

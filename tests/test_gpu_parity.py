@@ -372,3 +372,69 @@ def test_ur5_true_dimensions_vs_oracle(nh):
         gm, = torch.autograd.grad(mu.sum(), xs, retain_graph=True)
         gv, = torch.autograd.grad(var.sum(), xs)
         assert relmax(jm[:, e, :], gm.numpy()) < 1e-6 and relmax(jv[:, e, :], gv.numpy()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# opt-in INT8 tensor-core contraction with error compensation.  Stated tolerances: with 8 digit planes the
+# posterior variance agrees with the native fp64 path to 1e-7 relative, with 7 planes to 1e-5 (the north-star bound); the
+# contraction itself is exact up to the 2^-63 / 2^-55 representation of the operands relative to their row maxima.
+# ---------------------------------------------------------------------------------------------------------------------
+def _need_ozaki():
+    from mcpilco_b200 import _native as Nn
+    if not Nn.lib().mcpilco_ozaki_available():
+        pytest.skip("built without CUTLASS headers")
+
+
+@pytest.mark.parametrize("M,N", [(128, 128), (77, 300), (513, 1000)])
+def test_ozaki_contraction_matches_fp64_gemm(nh, M, N):
+    from mcpilco_b200 import _ops as ops
+    _need_ozaki()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, N, dtype=torch.float64, device="cuda", generator=g) * torch.logspace(-3, 3, M, dtype=torch.float64, device="cuda")[:, None]
+    B = torch.randn(N, N, dtype=torch.float64, device="cuda", generator=g) * torch.logspace(2, -2, N, dtype=torch.float64, device="cuda")[:, None]
+    ref = A @ B.t()
+    scale = A.abs().amax(1, keepdim=True) * B.abs().amax(1, keepdim=True).t() * N   # the error bound is relative to rowmax * colmax * K
+    # 8 planes: indistinguishable from the fp64 reference's own rounding (~2^-53 of the scale); 7 planes: 2^-55 operand truncation
+    for S, tol in ((8, 2.0 ** -52), (7, 2.0 ** -49)):
+        V, _, _ = ops.ozaki_matmul(A, B, S)
+        assert float(((V - ref).abs() / scale).max()) < tol, S
+
+
+@pytest.mark.parametrize("N,M", [(1000, 513), (2048, 700)])
+def test_ozaki_posterior_within_stated_tolerance(nh, N, M):
+    from mcpilco_b200 import _ops as ops
+    from mcpilco_b200 import _pack as P
+    _need_ozaki()
+    rs = np.random.RandomState(N)
+    spec = P.spec_from_dict({"D": 6, "log_ls": [2, 2, 2, 0.8, 1.5, 2.5], "lambda": 1.0, "mean": 0.0,
+                             "mpk": [np.exp([-5, -5, -5, -4, -4, -4, -3.0]), np.exp([-5, -5, -4, -2, -1, -4.0] * 2)], "sigma_n": 0.1})
+    gen = torch.Generator().manual_seed(N)
+    X, Y = O.cartpole_dataset(N, 0.1, gen)
+    Xg, yg = X.to("cuda:0"), Y[:, 0:1].contiguous().to("cuda:0")
+    alpha, Kinv = ops.gp_precompute(spec, Xg, yg)
+    Xs = (X[torch.randint(0, N, (M,), generator=gen)] + 0.05 * torch.randn(M, 6, dtype=torch.float64, generator=gen)).to("cuda:0")
+    m0, v0, jm0, jv0 = ops.gp_predict([ops.FittedGp(spec, Xg, alpha, Kinv, ozaki_slices=0)], Xs, jac=True)
+    for S, tol in ((8, 1e-7), (7, 1e-5)):
+        m1, v1, jm1, jv1 = ops.gp_predict([ops.FittedGp(spec, Xg, alpha, Kinv, ozaki_slices=S)], Xs, jac=True)
+        assert torch.equal(m1, m0) and torch.equal(jm1, jm0)          # the mean does not go through the contraction
+        assert float(((v1 - v0).abs() / v0.abs()).max()) < tol, (S, float(((v1 - v0).abs() / v0.abs()).max()))
+        assert relmax(jv1, jv0.cpu().numpy()) < tol
+    with pytest.raises(RuntimeError):
+        ops.FittedGp(spec, Xg, alpha, Kinv, ozaki_slices=5)
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+def test_ozaki_rollout_against_goldens(nh, name, monkeypatch):
+    """The whole rollout (per-step kernels, INT8 contraction with 8 planes) against the reference's trajectories, cost and gradients."""
+    _need_ozaki()
+    monkeypatch.setenv("MCPILCO_OZAKI", "8")
+    monkeypatch.setenv("MCPILCO_NO_SMALL_PATH", "1")
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    gps = nh.native_fit(sc)
+    assert all(gp.ozaki == 8 for gp in gps)
+    plan, states, inputs = _run_rollout(nh, sc, gps)
+    close(plan.cost_out[0], g["cost"], REL_VAL)
+    assert relmax(states, g["states"]) < REL_VAL
+    gr = plan.backward(grad_cost=1.0)
+    for k in ("log_ls", "centers", "W"):
+        assert relmax(gr[k], g["g_" + k]) < REL_GRAD
