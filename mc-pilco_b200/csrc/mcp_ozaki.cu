@@ -75,7 +75,7 @@ namespace {
 using namespace cute;
 using ElemAB = int8_t;
 using ElemC = int32_t;
-using TileShape_ = Shape<_256, _128, _128>;  // one MMA tile spans a CTA pair (cta_group::2): each SM holds 128 rows, B is shared
+using TileShape_ = Shape<_256, _256, _128>;  // one MMA tile spans a CTA pair (cta_group::2): each SM holds 128 rows, B is shared
 using ClusterShape_ = Shape<_2, _1, _1>;
 using Epi = typename cutlass::epilogue::collective::CollectiveBuilder<
     cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape_, ClusterShape_, cutlass::epilogue::collective::EpilogueTileAuto, ElemC,
