@@ -317,7 +317,7 @@ def own_arm(args):
     # ---- opt-in variants of the dominant contraction (same workload, same API; reported beside the fp64 headline) ----
     variants = {}
     from mcpilco_b200 import _native as _Nn
-    if not args.no_variants and args.ozaki == 0 and _Nn.lib().mcpilco_ozaki_available() and args.train_points * 8 <= 65536:
+    if not args.no_variants and args.ozaki == 0 and _Nn.lib().mcpilco_ozaki_available() and args.train_points >= 4096:
         for S, tol in ((8, "posterior variance within 1e-7 relative of the fp64 path (tests/test_gpu_parity.py)"),
                        (7, "posterior variance within 1e-5 relative of the fp64 path")):
             os.environ["MCPILCO_OZAKI"] = str(S)

@@ -256,7 +256,8 @@ int mcpilco_prof_read(double* total_ms, uint64_t* launches, double* flops);
 /* OPT-IN variant of the posterior contraction V = K* Kinv on the INT8 tensor cores (tcgen05) with error compensation (Ozaki scheme:
  * `slices` balanced base-256 digit planes per operand, exact int32 plane products, fp64 recombination).  slices = 8 reproduces the
  * fp64 contraction to ~1e-12 relative, slices = 7 to ~1e-9 (tolerances on the posterior variance: DESIGN.md).  prepare() slices one
- * GP's Kinv once per model update into caller-owned buffers that are then referenced from McpGp.  Requires N * slices <= 65536. */
+ * GP's Kinv once per model update into caller-owned buffers that are then referenced from McpGp.  The contraction index is cut into
+ * segments of at most 65536 / slices columns (exact int32 accumulation), recombined in fp64. */
 int mcpilco_ozaki_available(void);
 size_t mcpilco_ozaki_plane_bytes(int N, int slices);
 int mcpilco_ozaki_prepare(const double* Kinv, int N, int ld, int slices, int8_t* planes, int32_t* exponents, void* stream);

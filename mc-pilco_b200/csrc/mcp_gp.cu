@@ -734,10 +734,8 @@ extern "C" __attribute__((visibility("default"))) size_t mcpilco_gp_predict_work
   const int N = Nmax > 0 ? Nmax : 1;
   size_t per = 2 * (size_t)mcp::ld16(N) * sizeof(double);
   size_t fixed = 256;
-  if ((long long)N * 8 <= 65536) {
-    per += mcp::ozaki_scratch_bytes(1024, N, 8) / 1024 + 8;
-    fixed += 16384 * sizeof(double);
-  }
+  per += mcp::ozaki_scratch_bytes(1024, N, 8) / 1024 + 8;
+  fixed += 16384 * sizeof(double);
   const size_t m = (size_t)(M > 0 ? M : 1);
   size_t want = per * m;
   const size_t cap = (size_t)2 << 30, floor_ = per * 128;

@@ -6,7 +6,8 @@
 //     64-bit fixed-point integer F = rint(a 2^(8S - e)) and written as S balanced base-256 digits d_t in [-128, 127]
 //     (a 2^-e = sum_t d_t 256^-(t+1), exact to 2^-8S);
 //   * the product keeps the S(S+1)/2 digit-plane products with t + u < S:   A B^T = 2^(eA+eB) sum_w 256^-(w+2) C_w,
-//     C_w = sum_{t+u=w} A_t B_u^T, every C_w an EXACT int32 GEMM (|C_w| <= (w+1) K 2^14 < 2^31 for K <= 8192);
+//     C_w = sum_{t+u=w} A_t B_u^T, every C_w an EXACT int32 GEMM (|C_w| <= (w+1) K 2^14 < 2^31 as long as S K <= 65536; a longer
+//     contraction index is cut into segments that are recombined in fp64);
 //   * storing A's planes side by side along K and B's planes in REVERSE order makes every C_w ONE int8 GEMM with
 //     K_eff = (w+1) K over contiguous sub-ranges: S launches instead of S(S+1)/2, no read-modify-write of C;
 //   * a combine kernel sums the S int32 planes from the least significant up, in fp64, and applies the row/column scales.
@@ -28,9 +29,11 @@
 namespace mcp {
 
 // ---- slicing: one warp per row -----------------------------------------------------------------------------------
-// planes[row][p][k], p = t (reverse == 0) or S-1-t (reverse == 1); row stride S * Kp bytes; columns K..Kp-1 are zero.
-__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ A, int rows, int K, int ld, int S, int Kp, int reverse,
-                                                          int8_t* __restrict__ planes, int32_t* __restrict__ expo) {
+// The contraction index is cut into `nseg` segments of Ks columns (S * Ks <= 65536 keeps every int32 plane product exact); a segment's
+// planes are contiguous:  planes[row][seg][p][k],  p = t (reverse == 0) or S-1-t (reverse == 1), k < Ksp (Ks rounded up to 128, zero
+// padded).  Row stride nseg * S * Ksp bytes.  One exponent per row, common to all segments.
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ A, int rows, int K, int ld, int S, int Ks, int Ksp, int nseg,
+                                                          int reverse, int8_t* __restrict__ planes, int32_t* __restrict__ expo) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const double* a = A + (size_t)row * ld;
@@ -41,19 +44,20 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   const int e = (mx > 0.0 && isfinite(mx)) ? ilogb(mx) + 3 : 0;  // |a| 2^-e < 1/4: the most significant balanced digit stays within
                                                                    // [-65, 65] after the carries from below (no wrap at +128)
   if (lane == 0) expo[row] = e;
-  int8_t* out = planes + (size_t)row * S * Kp;
+  int8_t* out = planes + (size_t)row * nseg * S * Ksp;
   const int sh = 8 * S - e;
-  for (int k = lane; k < Kp; k += 32) {
+  for (int kk = lane; kk < nseg * Ksp; kk += 32) {
+    const int seg = kk / Ksp, k = kk - seg * Ksp, col = seg * Ks + k;
     long long F = 0;
-    if (k < K) {
-      const double v = a[k];
+    if (k < Ks && col < K) {
+      const double v = a[col];
       F = isfinite(v) ? __double2ll_rn(scalbn(v, sh)) : 0;  // |F| < 2^(8S-2) <= 2^62
     }
 #pragma unroll 1
     for (int t = S - 1; t >= 0; t--) {
       const long long d = ((F + 128) & 255) - 128;  // balanced digit in [-128, 127]
       F = (F - d) >> 8;
-      out[(size_t)(reverse ? S - 1 - t : t) * Kp + k] = (int8_t)d;
+      out[((size_t)seg * S + (reverse ? S - 1 - t : t)) * Ksp + k] = (int8_t)d;
     }
   }
 }
@@ -61,13 +65,14 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
 // ---- combine: V = 2^(eA + eB) sum_w 256^-(w+2) C_w, least significant plane first ---------------------------------
 __global__ void __launch_bounds__(256) ozaki_combine_kernel(const int32_t* __restrict__ C, size_t plane_stride, int ldc, int M, int N, int S,
                                                             const int32_t* __restrict__ eA, const int32_t* __restrict__ eB,
-                                                            double* __restrict__ V, int ldv) {
+                                                            double* __restrict__ V, int ldv, int accumulate) {
   const int n = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
   if (n >= N || m >= M) return;
   const int32_t* c = C + (size_t)m * ldc + n;
   double acc = 0.0;
   for (int w = S - 1; w >= 0; w--) acc = fma((double)c[(size_t)w * plane_stride], scalbn(1.0, -8 * (w + 2)), acc);
-  V[(size_t)m * ldv + n] = scalbn(acc, eA[m] + eB[n]);
+  const double v = scalbn(acc, eA[m] + eB[n]);
+  V[(size_t)m * ldv + n] = accumulate ? V[(size_t)m * ldv + n] + v : v;
 }
 
 #ifdef MCP_WITH_CUTLASS
@@ -112,10 +117,26 @@ static int int8_gemm(const int8_t* A, int lda, const int8_t* B, int ldb, int32_t
 }
 #endif
 
-int ozaki_kp(int K) { return (K + 127) / 128 * 128; }
+// segmentation of the contraction index: nseg segments of Ks columns, Ksp = Ks rounded up to the MMA K tile
+struct OzGeom {
+  int nseg, Ks, Ksp;
+};
+static OzGeom ozaki_geom(int K, int S) {
+  const int cap = 65536 / S / 128 * 128;  // S * Ks * 2^14 <= 2^30
+  OzGeom g;
+  g.nseg = (K + cap - 1) / cap;
+  g.Ks = ((K + g.nseg - 1) / g.nseg + 127) / 128 * 128;
+  if (g.Ks > cap) g.Ks = cap;
+  g.nseg = (K + g.Ks - 1) / g.Ks;
+  g.Ksp = g.Ks;
+  return g;
+}
 
 // bytes of the digit planes of a [rows x K] matrix with S slices
-size_t ozaki_plane_bytes(int rows, int K, int S) { return (size_t)rows * S * ozaki_kp(K); }
+size_t ozaki_plane_bytes(int rows, int K, int S) {
+  const OzGeom g = ozaki_geom(K, S);
+  return (size_t)rows * g.nseg * S * g.Ksp;
+}
 
 // scratch for one contraction of mc particles against N points: A planes + A exponents + S int32 planes + gemm workspace
 size_t ozaki_scratch_bytes(int mc, int N, int S) {
@@ -124,9 +145,9 @@ size_t ozaki_scratch_bytes(int mc, int N, int S) {
 
 int ozaki_slice(const double* A, int rows, int K, int ld, int S, int reverse, int8_t* planes, int32_t* expo, cudaStream_t st) {
   MCP_CHECK_ARG(S >= 2 && S <= 8, "ozaki: slices %d outside [2, 8]", S);
-  MCP_CHECK_ARG((long long)S * K <= (1ll << 16), "ozaki: S * K = %lld exceeds 65536 (int32 accumulation bound)", (long long)S * K);
   if (rows <= 0) return MCP_OK;
-  ozaki_slice_kernel<<<cdiv(rows, 8), 256, 0, st>>>(A, rows, K, ld, S, ozaki_kp(K), reverse, planes, expo);
+  const OzGeom g = ozaki_geom(K, S);
+  ozaki_slice_kernel<<<cdiv(rows, 8), 256, 0, st>>>(A, rows, K, ld, S, g.Ks, g.Ksp, g.nseg, reverse, planes, expo);
   MCP_LAUNCH_CHECK();
   return MCP_OK;
 }
@@ -136,7 +157,8 @@ int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t*
                    size_t scratch_bytes, cudaStream_t st) {
 #ifdef MCP_WITH_CUTLASS
   MCP_CHECK_ARG(scratch_bytes >= ozaki_scratch_bytes(mc, N, S), "ozaki: scratch too small");
-  const int Kp = ozaki_kp(N), ldc = (int)align_up((size_t)N, 4);
+  const OzGeom gm = ozaki_geom(N, S);
+  const int ldc = (int)align_up((size_t)N, 4), lda8 = gm.nseg * S * gm.Ksp;
   char* p = (char*)align_up((size_t)scratch, 256);
   int8_t* Ap = (int8_t*)p; p += align_up(ozaki_plane_bytes(mc, N, S), 256);
   int32_t* Ae = (int32_t*)p; p += align_up((size_t)mc * 4, 256);
@@ -144,13 +166,18 @@ int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t*
   void* gws = (void*)align_up((size_t)p, 256);
   const size_t plane_stride = (size_t)mc * ldc;
   if (int e = ozaki_slice(A, mc, N, lda, S, 0, Ap, Ae, st)) return e;
-  for (int w = 0; w < S; w++) {
-    // C_w = [A_0 .. A_w] * [B_w .. B_0]^T : A planes 0..w are the first (w+1) Kp columns; reversed B planes S-1-w .. S-1 the last ones
-    if (int e = int8_gemm(Ap, S * Kp, Bplanes + (size_t)(S - 1 - w) * Kp, S * Kp, C + w * plane_stride, ldc, mc, N, (w + 1) * Kp, gws, 65536, st))
-      return e;
+  for (int seg = 0; seg < gm.nseg; seg++) {
+    const int8_t* As = Ap + (size_t)seg * S * gm.Ksp;
+    const int8_t* Bs = Bplanes + (size_t)seg * S * gm.Ksp;
+    for (int w = 0; w < S; w++) {
+      // C_w = [A_0 .. A_w] * [B_w .. B_0]^T : A planes 0..w are the first (w+1) Ksp columns of the segment; the reversed B planes
+      // S-1-w .. S-1 are its last ones
+      if (int e = int8_gemm(As, lda8, Bs + (size_t)(S - 1 - w) * gm.Ksp, lda8, C + w * plane_stride, ldc, mc, N, (w + 1) * gm.Ksp, gws, 65536, st))
+        return e;
+    }
+    ozaki_combine_kernel<<<dim3(cdiv(N, 256), mc), 256, 0, st>>>(C, plane_stride, ldc, mc, N, S, Ae, Bexp, V, ldv, seg > 0);
+    MCP_LAUNCH_CHECK();
   }
-  ozaki_combine_kernel<<<dim3(cdiv(N, 256), mc), 256, 0, st>>>(C, plane_stride, ldc, mc, N, S, Ae, Bexp, V, ldv);
-  MCP_LAUNCH_CHECK();
   return MCP_OK;
 #else
   set_error("ozaki: this build has no CUTLASS headers (MCP_WITH_CUTLASS undefined)");

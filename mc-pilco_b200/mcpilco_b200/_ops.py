@@ -154,8 +154,8 @@ class FittedGp:
             L = _enter(self.Xtr.device)
             if not L.mcpilco_ozaki_available():
                 raise RuntimeError("mcpilco_b200: the INT8 (Ozaki) contraction was requested but this build has no CUTLASS headers")
-            if self.ozaki not in (7, 8) or self.N * self.ozaki > 65536:
-                raise RuntimeError("mcpilco_b200: ozaki_slices must be 7 or 8 with N * slices <= 65536 (N = %d)" % self.N)
+            if self.ozaki not in (7, 8):
+                raise RuntimeError("mcpilco_b200: ozaki_slices must be 7 or 8")
             self.planes = torch.empty(L.mcpilco_ozaki_plane_bytes(self.N, self.ozaki), dtype=torch.uint8, device=self.Xtr.device)
             self.plane_exp = torch.empty(self.N, dtype=torch.int32, device=self.Xtr.device)
             N.check(L.mcpilco_ozaki_prepare(_ptr(self.Kinv), self.N, self.ld, self.ozaki, _ptr(self.planes), _ptr(self.plane_exp),

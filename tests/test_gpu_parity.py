@@ -385,7 +385,7 @@ def _need_ozaki():
         pytest.skip("built without CUTLASS headers")
 
 
-@pytest.mark.parametrize("M,N", [(128, 128), (77, 300), (513, 1000)])
+@pytest.mark.parametrize("M,N", [(128, 128), (77, 300), (513, 1000), (64, 8320)])  # the last one needs two K segments
 def test_ozaki_contraction_matches_fp64_gemm(nh, M, N):
     from mcpilco_b200 import _ops as ops
     _need_ozaki()
