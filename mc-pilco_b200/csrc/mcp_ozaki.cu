@@ -46,18 +46,28 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   if (lane == 0) expo[row] = e;
   int8_t* out = planes + (size_t)row * nseg * S * Ksp;
   const int sh = 8 * S - e;
-  for (int kk = lane; kk < nseg * Ksp; kk += 32) {
+  // four consecutive columns per lane: one packed 32-bit store per plane (Ksp is a multiple of 128, so groups never straddle a segment)
+  for (int kk = lane * 4; kk < nseg * Ksp; kk += 128) {
     const int seg = kk / Ksp, k = kk - seg * Ksp, col = seg * Ks + k;
-    long long F = 0;
-    if (k < Ks && col < K) {
-      const double v = a[col];
-      F = isfinite(v) ? __double2ll_rn(scalbn(v, sh)) : 0;  // |F| < 2^(8S-2) <= 2^62
+    long long F[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      F[i] = 0;
+      if (k + i < Ks && col + i < K) {
+        const double v = a[col + i];
+        F[i] = isfinite(v) ? __double2ll_rn(scalbn(v, sh)) : 0;  // |F| < 2^(8S-2) <= 2^62
+      }
     }
 #pragma unroll 1
     for (int t = S - 1; t >= 0; t--) {
-      const long long d = ((F + 128) & 255) - 128;  // balanced digit in [-128, 127]
-      F = (F - d) >> 8;
-      out[((size_t)seg * S + (reverse ? S - 1 - t : t)) * Ksp + k] = (int8_t)d;
+      unsigned packed = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const long long d = ((F[i] + 128) & 255) - 128;  // balanced digit in [-128, 127]
+        F[i] = (F[i] - d) >> 8;
+        packed |= ((unsigned)d & 255u) << (8 * i);
+      }
+      *reinterpret_cast<unsigned*>(out + ((size_t)seg * S + (reverse ? S - 1 - t : t)) * Ksp + k) = packed;
     }
   }
 }
@@ -66,13 +76,28 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
 __global__ void __launch_bounds__(256) ozaki_combine_kernel(const int32_t* __restrict__ C, size_t plane_stride, int ldc, int M, int N, int S,
                                                             const int32_t* __restrict__ eA, const int32_t* __restrict__ eB,
                                                             double* __restrict__ V, int ldv, int accumulate) {
-  const int n = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
+  // four consecutive columns per thread (ldc is a multiple of 4: 16-byte plane loads)
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4, m = blockIdx.y;
   if (n >= N || m >= M) return;
   const int32_t* c = C + (size_t)m * ldc + n;
-  double acc = 0.0;
-  for (int w = S - 1; w >= 0; w--) acc = fma((double)c[(size_t)w * plane_stride], scalbn(1.0, -8 * (w + 2)), acc);
-  const double v = scalbn(acc, eA[m] + eB[n]);
-  V[(size_t)m * ldv + n] = accumulate ? V[(size_t)m * ldv + n] + v : v;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int w = S - 1; w >= 0; w--) {
+    const int4 q = *reinterpret_cast<const int4*>(c + (size_t)w * plane_stride);
+    const double sc = scalbn(1.0, -8 * (w + 2));
+    acc[0] = fma((double)q.x, sc, acc[0]);
+    acc[1] = fma((double)q.y, sc, acc[1]);
+    acc[2] = fma((double)q.z, sc, acc[2]);
+    acc[3] = fma((double)q.w, sc, acc[3]);
+  }
+  const int ea = eA[m];
+  double* out = V + (size_t)m * ldv + n;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (n + i < N) {
+      const double v = scalbn(acc[i], ea + eB[n + i]);
+      out[i] = accumulate ? out[i] + v : v;
+    }
+  }
 }
 
 #ifdef MCP_WITH_CUTLASS
@@ -175,7 +200,7 @@ int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t*
       if (int e = int8_gemm(As, lda8, Bs + (size_t)(S - 1 - w) * gm.Ksp, lda8, C + w * plane_stride, ldc, mc, N, (w + 1) * gm.Ksp, gws, 65536, st))
         return e;
     }
-    ozaki_combine_kernel<<<dim3(cdiv(N, 256), mc), 256, 0, st>>>(C, plane_stride, ldc, mc, N, S, Ae, Bexp, V, ldv, seg > 0);
+    ozaki_combine_kernel<<<dim3(cdiv(N, 1024), mc), 256, 0, st>>>(C, plane_stride, ldc, mc, N, S, Ae, Bexp, V, ldv, seg > 0);
     MCP_LAUNCH_CHECK();
   }
   return MCP_OK;
