@@ -192,10 +192,11 @@ class MC_PILCO(torch.nn.Module):
                          opt_steps_list, lr_list, f_optimizer, num_step_print=10, policy_reinit_dict=None, p_dropout_list=None,
                          std_cost_filt_order=None, std_cost_filt_cutoff=None, max_std_cost=None, alpha_cost=0.99, alpha_input=0.99,
                          alpha_diff_cost=0.99, lr_reduction_ratio=0.5, lr_min=0.001, p_drop_reduction=0.0, min_diff_cost=0.1,
-                         num_min_diff_cost=200, min_step=np.inf):
+                         num_min_diff_cost=200, min_step=np.inf, max_reinit=np.inf):
         """Gradient-based policy improvement on the particle cost (reference :375-613): optimiser built from the eval'd
         `f_optimizer` string, NaN re-sampling (<= 10 attempts) and policy re-initialisation, exponential monitors of the cost
-        decrease driving learning-rate halving, dropout reduction and early exit."""
+        decrease driving learning-rate halving, dropout reduction and early exit.  `max_reinit` (not in the reference, default
+        unlimited like the reference) bounds the number of NaN-triggered policy re-initialisations."""
         H = int(T_control / self.T_sampling)
         n_steps = opt_steps_list[trial_index]
         p_drop0 = 0.0 if p_dropout_list is None else p_dropout_list[trial_index]
@@ -269,6 +270,8 @@ class MC_PILCO(torch.nn.Module):
             s["done"] += 1
             if is_nan:  # ten NaN rollouts in a row: new random policy, restart the optimisation
                 reinit_counter += 1
+                if reinit_counter > max_reinit:
+                    raise RuntimeError("reinforce_policy: the particle cost stayed NaN through %d policy re-initialisations" % (reinit_counter - 1))
                 print("\nCost is NaN: re-initialize control policy [attempt #" + str(reinit_counter) + "]")
                 self.control_policy.reinit(**policy_reinit_dict)
                 s = fresh()

@@ -305,3 +305,19 @@ def test_mean_rollout_along_recorded_inputs(R):
         x, _, _ = O.next_state(Hh.oracle_model(sc), gps, x, Hh.T(g["inputs"][t - 1:t, 0, :]), None, particle_pred=False)
         ref.append(x)
     np.testing.assert_allclose(traj, torch.cat(ref).numpy(), rtol=1e-6, atol=1e-9)
+
+
+def test_example_trial_loop_runs():
+    """examples/cartpole_swingup.py: data -> GP training -> policy optimisation -> apply, twice, all through the mirrored class API."""
+    import os, subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "cartpole_swingup.py"), "--trials", "2", "--opt-steps", "40", "--gp-epochs", "60"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("trial ")]
+    assert len(lines) == 2
+    import re
+    c0, c1 = map(float, re.search(r"particle cost ([0-9.]+) -> ([0-9.]+)", lines[0]).groups())
+    assert c1 < c0
