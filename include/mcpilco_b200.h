@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 4
+#define MCP_ABI_VERSION 5
 
 #define MCP_MAX_D 32    /* gp-input dimension            */
 #define MCP_MAX_DS 16   /* state dimension               */
@@ -204,6 +204,14 @@ int mcpilco_gp_diag_covariance(const McpGpSpec* spec, const double* X, int n, do
 size_t mcpilco_gp_precompute_workspace_bytes(int N);
 int mcpilco_gp_precompute(const McpGpSpec* spec, const double* Xtr, const double* y, int N, double* alpha,
                           double* Kinv, int ld, double* Lfac, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Greedy subset-of-data selection (GP_prior.get_SOD, gpr_lib/GP_prior/GP_prior.py:232-257): candidates are visited in `order`
+ * (DEVICE int array [N], NULL = 0..N-1; order[0] seeds the subset); a candidate joins when the predictive standard deviation of the
+ * GP fitted on the current subset exceeds `threshold` at it.  idx_out [N] receives the selected indices, *count_out their number
+ * (both DEVICE).  One incremental Cholesky factor instead of a refit per candidate; no host synchronisation inside. */
+size_t mcpilco_gp_sod_workspace_bytes(int N);
+int mcpilco_gp_sod_select(const McpGpSpec* spec, const double* X, int N, const int* order, double threshold, int* idx_out, int* count_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Training objective of the GP hyper-parameters and its analytic gradient:
  *   out[0] = 0.5 ((y - m)^T K^-1 (y - m) + log det K)   (Marginal_log_likelihood.forward, gpr_lib/Likelihood/Gaussian_likelihood.py:12-24,

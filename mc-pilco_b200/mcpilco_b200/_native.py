@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 MAX_D, MAX_DS, MAX_DU, MAX_E, MAX_DP, MAX_POLY, MAX_DEG = 32, 16, 8, 16, 32, 3, 3
-ABI_VERSION = 4
+ABI_VERSION = 5
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcpilco_b200.so")
 
@@ -80,6 +80,9 @@ SYMBOLS = {
     "mcpilco_gp_precompute_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mcpilco_gp_precompute": (C.c_int, [C.POINTER(GpSpec), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mcpilco_gp_sod_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "mcpilco_gp_sod_select": (C.c_int, [C.POINTER(GpSpec), C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     "mcpilco_gp_nlml_grad_size": (C.c_int, []),
     "mcpilco_gp_nlml_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mcpilco_gp_nlml": (C.c_int, [C.POINTER(GpSpec), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

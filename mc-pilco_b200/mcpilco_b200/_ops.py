@@ -113,6 +113,25 @@ def gp_nlml(spec, Xtr, y):
     return out
 
 
+def gp_sod_select(spec, X, threshold, order=None):
+    """Greedy subset-of-data selection on the device; returns the selected indices (python list, in selection order).
+    GP_prior.py:232-257."""
+    X = _c(X, "X")
+    L_ = _enter(X.device)
+    n = X.shape[0]
+    if n < 1 or X.shape[1] != spec.D:
+        raise RuntimeError("gp_sod_select: X must be [N>=1, %d]" % spec.D)
+    idx = torch.empty(n, dtype=torch.int32, device=X.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=X.device)
+    od = None if order is None else torch.as_tensor(order, dtype=torch.int32, device=X.device).contiguous()
+    wsb = L_.mcpilco_gp_sod_workspace_bytes(n)
+    ws = _workspace(X.device, wsb, "sod")
+    N.check(L_.mcpilco_gp_sod_select(C.byref(spec), _ptr(X), n, _ptr(od), float(threshold), _ptr(idx), _ptr(cnt), _ptr(ws), ws.numel(),
+                                     _stream(X.device)))
+    k = int(cnt.item())
+    return [int(i) for i in idx[:k].tolist()]
+
+
 NLML_LAMBDA, NLML_MEAN, NLML_SN2, NLML_ILS = 1, 2, 3, 4
 
 

@@ -171,22 +171,16 @@ class GP_prior(torch.nn.Module):
         return Y_hat, var, alpha
 
     def get_SOD(self, X, Y, threshold, flg_permutation=False):
-        """Greedy subset of data: a point joins the subset when the predictive std of the GP fitted on the current
-        subset exceeds `threshold` at it (reference :232-257).  Every refit / prediction is a native call; the
-        threshold test is the one host sync per candidate."""
+        """Greedy subset of data: a point joins the subset when the predictive std of the GP fitted on the current subset exceeds
+        `threshold` at it (reference :232-257; the first sample always seeds the subset, the rest are visited in order or in a random
+        permutation).  One native call: the Cholesky factor of the subset is grown row by row on the device instead of refitting per
+        candidate (the prior mean does not enter the variance, so Y is not needed)."""
         n = X.shape[0]
-        rest = (1 + torch.randperm(n - 1)).tolist() if flg_permutation else list(range(1, n))
-        order = [0] + rest  # the first sample always seeds the subset
-        chosen = [0]
+        order = None
+        if flg_permutation:
+            order = [0] + (1 + torch.randperm(n - 1)).tolist()
         thr = float(P._np(threshold).reshape(-1)[0])
-        spec = self.gp_spec(X.shape[1])
-        for i in order[1:]:
-            idx = torch.as_tensor(chosen, device=X.device)
-            alpha, K_inv = ops.gp_precompute(spec, X[idx, :], Y[idx, :])
-            _, var = ops.gp_predict([ops.FittedGp(spec, X[idx, :], alpha, K_inv)], X[i:i + 1, :])
-            if float(torch.sqrt(var[0, 0])) > thr:
-                chosen.append(i)
-        return chosen
+        return ops.gp_sod_select(self.gp_spec(X.shape[1]), X, thr, order)
 
     def nlml(self, X, Y):
         """0.5 ((Y - m)^T K^-1 (Y - m) + log det K) as a [1, 1] tensor whose backward fills the hyper-parameter gradients."""

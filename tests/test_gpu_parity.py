@@ -438,3 +438,27 @@ def test_ozaki_rollout_against_goldens(nh, name, monkeypatch):
     gr = plan.backward(grad_cost=1.0)
     for k in ("log_ls", "centers", "W"):
         assert relmax(gr[k], g["g_" + k]) < REL_GRAD
+
+
+@pytest.mark.parametrize("kernel", ["se", "se+mpk"])
+def test_sod_selection_vs_oracle(nh, kernel):
+    """Device-side incremental greedy selection against the oracle's refit-per-candidate loop (reference GP_prior.py:232-257), in the
+    natural order and in a given permutation."""
+    from mcpilco_b200 import _ops as ops
+    from mcpilco_b200 import _pack as P
+    rs = np.random.RandomState(11)
+    N = 140
+    sc = scenarios.scenario("c1")
+    X = np.concatenate([sc["X"], sc["X"][rs.choice(48, N - 48)] + 0.3 * rs.randn(N - 48, 6)], 0)
+    mpk = [np.exp([-5, -5, -5, -4, -4, -4, -3.0]), np.exp([-5, -5, -4, -2, -1, -4.0] * 2)] if kernel == "se+mpk" else []
+    log_ls = [2, 2, 2, 0.8, 1.5, 2.5]
+    spec = P.spec_from_dict({"D": 6, "log_ls": log_ls, "lambda": 1.0, "mean": 0.0, "mpk": mpk, "sigma_n": 0.05})
+    so = O.make_spec(6, log_ls=log_ls, mpk_log_pars=[np.log(w) for w in mpk], sigma_n=0.05)
+    thr = 0.1  # selects ~100 of the 140 points: many accept/reject decisions, some close to the threshold
+    Y = Hh.T(rs.randn(N, 1))
+    ref = O.sod_select(so, Hh.T(X), Y, thr)
+    got = ops.gp_sod_select(spec, nh.G(X), thr)
+    assert got == ref and 1 < len(ref) < N
+    perm = [0] + (1 + rs.permutation(N - 1)).tolist()
+    ref_p = [perm[i] for i in O.sod_select(so, Hh.T(X[perm]), Y, thr)]
+    assert ops.gp_sod_select(spec, nh.G(X), thr, order=perm) == ref_p
