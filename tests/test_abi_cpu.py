@@ -127,3 +127,35 @@ def test_class_kernel_terms_match_flat_packing():
     # a scalar (non-ARD) lengthscale broadcasts over the active dimensions
     iso = SGP.RBF(np.arange(3), lengthscales_init=np.array([2.0]), sigma_n_init=np.array([0.1])).gp_spec(3)
     assert list(iso.inv_ls)[:3] == [0.5, 0.5, 0.5]
+
+
+def test_argument_errors_are_reported_before_any_cuda_work(native):
+    """Entry points validate their arguments first: bad shapes / null pointers return MCP_E_ARG with a message, on a box with or
+    without a GPU (nothing is launched)."""
+    from mcpilco_b200 import _pack as P
+    L = native.lib()
+    spec = P.spec_from_dict({"D": 3, "log_ls": [0.0, 0.0, 0.0], "sigma_n": 0.1})
+    E_ARG = -1
+    assert L.mcpilco_gp_covariance(None, None, 4, None, 4, 0, None, 4, None) == E_ARG and b"null gp spec" in L.mcpilco_last_error()
+    bad = P.spec_from_dict({"D": 3, "log_ls": [0.0, 0.0, 0.0], "sigma_n": 0.1}); bad.D = 99
+    assert L.mcpilco_gp_covariance(C.byref(bad), None, 4, None, 4, 0, None, 4, None) == E_ARG and b"gp input dim 99" in L.mcpilco_last_error()
+    empty = P.new_gp_spec(3)
+    assert L.mcpilco_gp_diag_covariance(C.byref(empty), None, 4, None, None) == E_ARG and b"empty kernel" in L.mcpilco_last_error()
+    assert L.mcpilco_gp_precompute(C.byref(spec), None, None, 0, None, None, 0, None, None, 0, None) == E_ARG
+    assert L.mcpilco_gp_predict(None, 0, None, 5, None, None, None, None, None, 0, None) == E_ARG and b"bad E" in L.mcpilco_last_error()
+    assert L.mcpilco_gp_nlml(C.byref(spec), None, None, 5, None, None, 0, None) == E_ARG
+    assert L.mcpilco_gp_sod_select(C.byref(spec), None, 5, None, 0.1, None, None, None, 0, None) == E_ARG
+    assert L.mcpilco_rollout_fwd(None, None) == E_ARG and b"null rollout descriptor" in L.mcpilco_last_error()
+    r = native.Rollout()
+    r.M, r.H = 0, 5
+    assert L.mcpilco_rollout_fwd(C.byref(r), None) == E_ARG and b"M=0" in L.mcpilco_last_error()
+    r.M = 4
+    r.model.Ds, r.model.Du, r.model.E, r.model.D = 4, 1, 2, 7   # feature map would give 5
+    assert L.mcpilco_rollout_fwd(C.byref(r), None) == E_ARG and b"does not match the feature map" in L.mcpilco_last_error()
+    assert L.mcpilco_policy_forward(None, 3, 0, None, 0.0, None, 0, 0, None, None) == E_ARG
+    assert L.mcpilco_init_particles(2, None, None, 1, 4, 4, 0, 0, None, None) == E_ARG
+    assert L.mcpilco_ozaki_prepare(None, 4, 4, 8, None, None, None) == E_ARG
+    # workspace queries are pure host arithmetic
+    assert L.mcpilco_gp_precompute_workspace_bytes(300) > 2 * 320 * 320 * 8
+    assert L.mcpilco_rollout_workspace_bytes(400, 60, 2, 6, 300, 200, 5, 1) > 0 and L.mcpilco_gp_nlml_grad_size() == 4 + 32 + 9 * 33
+    assert L.mcpilco_ozaki_plane_bytes(8192, 8) == 8192 * 8 * 8192 and L.mcpilco_ozaki_plane_bytes(16384, 8) == 16384 * 2 * 8 * 8192
