@@ -396,29 +396,32 @@ __global__ void __launch_bounds__(256) posterior_reduce_kernel(const __grid_cons
 // for the two weight channels a = alpha (mean) and a = V (variance).  Per (particle, training point) this is ~4D+5 FMAs per
 // channel plus one kernel evaluation (5D + exp), about 2.2x fewer FP64 instructions than differentiating k point by point.
 // NP = number of polynomial terms; term p has degree p + 1 (get_Volterra_MPK_GP, Sparse_GP.py:671-737).
-constexpr int RED_TILE = 256;  // training points staged per tile
+constexpr int RED_TILE = 256;    // training points staged per tile
+constexpr int RED_THREADS = 128;  // 4 particles per block: with ~240 registers per thread two blocks share an SM, so one block's
+                                  // barriers and cp.async waits overlap with the other's FP64 work
 template <int DT, int NP>
-__global__ void __launch_bounds__(256) posterior_reduce_fast_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
+__global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
                                                                     int M, const double* __restrict__ Xtr,
                                                                     const double* __restrict__ alpha, int N,
                                                                     const double* __restrict__ V, int ldv, double var_scale, int E,
                                                                     int e, double* __restrict__ mean, double* __restrict__ var,
                                                                     double* __restrict__ jmean, double* __restrict__ jvar) {
   // training inputs (transposed: sY[buf][j][i], conflict-free for lane <-> point) and alpha, double-buffered by cp.async;
-  // the 8 warps of the block (8 particles) share them
+  // the warps of the block (one particle each) share them
   __shared__ double sY[2][DT][RED_TILE];
   __shared__ double sA[2][RED_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int m = min(blockIdx.x * 8 + warp, M - 1);  // surplus warps shadow the last particle (they still help staging)
-  const bool owner = blockIdx.x * 8 + warp < M;
+  constexpr int PB = RED_THREADS / 32;  // particles per block
+  const int m = min(blockIdx.x * PB + warp, M - 1);  // surplus warps shadow the last particle (they still help staging)
+  const bool owner = blockIdx.x * PB + warp < M;
   const int D = s.D;
   auto stage = [&](int t, int buf) {
     const int n0 = t * RED_TILE;
-    for (int el = tid; el < RED_TILE * D; el += 256) {
+    for (int el = tid; el < RED_TILE * D; el += RED_THREADS) {
       const int i = el / D, j = el - i * D;
       cp_async8(&sY[buf][j][i], Xtr + (size_t)min(n0 + i, N - 1) * D + j, (n0 + i < N) ? 8 : 0);
     }
-    cp_async8(&sA[buf][tid], alpha + min(n0 + tid, N - 1), (n0 + tid < N) ? 8 : 0);
+    for (int i = tid; i < RED_TILE; i += RED_THREADS) cp_async8(&sA[buf][i], alpha + min(n0 + i, N - 1), (n0 + i < N) ? 8 : 0);
     cp_async_commit();
   };
   double x[DT], xs[DT];
@@ -702,7 +705,7 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     double* jv = jac ? jvar + (size_t)m0 * E * g.spec.D : nullptr;
     if (jac && fast_reduce_ok(g.spec)) {
 #define MCP_FAST_REDUCE(DT_, NP_)                                                                                                   \
-  posterior_reduce_fast_kernel<DT_, NP_><<<grid, 256, 0, st>>>(g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e,          \
+  posterior_reduce_fast_kernel<DT_, NP_><<<cdiv(mc, RED_THREADS / 32), RED_THREADS, 0, st>>>(g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e,          \
                                                                mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv)
       const int np_ = g.spec.n_poly;
       if (g.spec.D <= 4) { if (np_ == 0) MCP_FAST_REDUCE(4, 0); else if (np_ == 1) MCP_FAST_REDUCE(4, 1); else MCP_FAST_REDUCE(4, 2); }
