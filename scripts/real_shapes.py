@@ -39,6 +39,9 @@ def scale_scenario(name, N, M, H, nb, rs):
     return sc
 
 
+LAST_FWD_MS = 0.0
+
+
 def time_gpu(sc, reps=20):
     gps = nh.native_fit(sc)
     plan, _ = nh.native_plan(sc, gps, need_grad=True, inject=False, seed=1)
@@ -52,7 +55,14 @@ def time_gpu(sc, reps=20):
         plan.forward(x0); plan.backward(grad_cost=1.0)
     e1.record(); torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / reps
-    return e0.elapsed_time(e1) / reps, wall * 1e3, float(plan.cost_out[0])
+    total = e0.elapsed_time(e1) / reps
+    e0.record()
+    for _ in range(reps):
+        plan.forward(x0)
+    e1.record(); torch.cuda.synchronize()
+    global LAST_FWD_MS
+    LAST_FWD_MS = e0.elapsed_time(e1) / reps
+    return total, wall * 1e3, float(plan.cost_out[0])
 
 
 def time_cpu(sc, threads, reps=2):
@@ -76,6 +86,7 @@ def main():
         sc = scale_scenario(name, N, M, H, nb, rs)
         g_ms, g_wall, cost = time_gpu(sc, reps)
         row = {"config": name, "N": N, "M": M, "H": H, "nb": nb, "gpu_ms_fwd_bwd": round(g_ms, 3), "gpu_wall_ms": round(g_wall, 3),
+               "gpu_ms_fwd": round(LAST_FWD_MS, 3), "gpu_ms_bwd": round(g_ms - LAST_FWD_MS, 3),
                "gpu_particle_steps_per_s": round(M * H / (g_ms * 1e-3)), "cost": cost}
         if "--no-cpu" not in sys.argv:
             c1 = time_cpu(sc, 1); call = time_cpu(sc, os.cpu_count())
