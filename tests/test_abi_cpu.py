@@ -159,3 +159,30 @@ def test_argument_errors_are_reported_before_any_cuda_work(native):
     assert L.mcpilco_gp_precompute_workspace_bytes(300) > 2 * 320 * 320 * 8
     assert L.mcpilco_rollout_workspace_bytes(400, 60, 2, 6, 300, 200, 5, 1) > 0 and L.mcpilco_gp_nlml_grad_size() == 4 + 32 + 9 * 33
     assert L.mcpilco_ozaki_plane_bytes(8192, 8) == 8192 * 8 * 8192 and L.mcpilco_ozaki_plane_bytes(16384, 8) == 16384 * 2 * 8 * 8192
+
+
+def test_torch_custom_ops_registered_and_shape_checked():
+    """torch.ops.mcpilco.* exist, infer shapes on meta/fake tensors, and refuse CPU tensors (no CPU implementation)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from mcpilco_b200 import _pack as P
+    from mcpilco_b200 import torch_ops as TO
+    spec = P.spec_from_dict({"D": 3, "log_ls": [0.0, 0.1, 0.2], "sigma_n": 0.1, "mpk": [[[1.0, 2.0, 3.0, 0.5]]]})
+    t = TO.spec_tensor(spec)
+    back = TO._spec(t)
+    assert bytes(back) == bytes(spec)
+    for name in ("gp_covariance", "gp_diag_covariance", "gp_precompute", "gp_predict", "gp_predict_jac", "gp_nlml"):
+        assert hasattr(torch.ops.mcpilco, name)
+    with FakeTensorMode(allow_non_fake_inputs=True):
+        X, Xs = torch.empty(10, 3, dtype=torch.float64), torch.empty(7, 3, dtype=torch.float64)
+        y = torch.empty(10, 1, dtype=torch.float64)
+        assert torch.ops.mcpilco.gp_covariance(t, X, Xs, False).shape == (10, 7)
+        a, Ki = torch.ops.mcpilco.gp_precompute(t, X, y)
+        assert a.shape == (10, 1) and Ki.shape == (10, 10)
+        m, v, jm, jv = torch.ops.mcpilco.gp_predict_jac(t, X, a, Ki, Xs, 1.0)
+        assert m.shape == (7, 1) and jv.shape == (7, 3)
+        assert torch.ops.mcpilco.gp_nlml(t, X, y).numel() == 4 + 32 + 3 * 3 * 33
+    with pytest.raises(NotImplementedError):
+        torch.ops.mcpilco.gp_covariance(t, torch.zeros(4, 3, dtype=torch.float64), None, False)
+    with pytest.raises(RuntimeError):
+        TO._spec(torch.zeros(5, dtype=torch.uint8))

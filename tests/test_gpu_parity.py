@@ -462,3 +462,28 @@ def test_sod_selection_vs_oracle(nh, kernel):
     perm = [0] + (1 + rs.permutation(N - 1)).tolist()
     ref_p = [perm[i] for i in O.sod_select(so, Hh.T(X[perm]), Y, thr)]
     assert ops.gp_sod_select(spec, nh.G(X), thr, order=perm) == ref_p
+
+
+@pytest.mark.parametrize("name", ["c1", "c4"])
+def test_torch_custom_ops_match_goldens(nh, name):
+    """torch.ops.mcpilco.* (torch.library layer over the C ABI) against the reference's golden vectors and the flat operators."""
+    from mcpilco_b200 import _ops as ops
+    from mcpilco_b200 import torch_ops as TO
+    sc, g = scenarios.scenario(name), Hh.load_golden(name)
+    X, Xs = nh.G(sc["X"]), nh.G(g["Xs"])
+    for e, sp in enumerate(nh.native_specs(sc)):
+        t, y = TO.spec_tensor(sp), nh.G(sc["Y"][:, e:e + 1])
+        close(torch.ops.mcpilco.gp_covariance(t, Xs, X, False), g[f"Kss_{e}"], 1e-12, 1e-15)
+        close(torch.ops.mcpilco.gp_covariance(t, X, None, True), g[f"Knoise_{e}"], 1e-12, 1e-15)
+        close(torch.ops.mcpilco.gp_diag_covariance(t, Xs), g[f"kdiag_{e}"], 1e-12)
+        alpha, Kinv = torch.ops.mcpilco.gp_precompute(t, X, y)
+        close(alpha, g[f"alpha_{e}"], 1e-7, 1e-7 * np.abs(g[f"alpha_{e}"]).max())
+        ga, gK = nh.G(g[f"alpha_{e}"]), nh.G(g[f"Kinv_{e}"])
+        m, v, jm, jv = torch.ops.mcpilco.gp_predict_jac(t, X, ga, gK, Xs, 1.0)
+        m2, v2 = torch.ops.mcpilco.gp_predict(t, X, ga, gK, Xs, 1.0)
+        close(m, g[f"pmean_{e}"], 1e-10, 1e-13)
+        close(v[:, 0], g[f"pvar_{e}"], 1e-8, 1e-13)
+        rm, rv, rjm, rjv = ops.gp_predict([ops.FittedGp(sp, X, ga, gK)], Xs, jac=True)
+        assert torch.equal(m, rm) and torch.equal(v, rv) and torch.equal(m2, rm) and torch.equal(v2, rv)
+        assert torch.equal(jm, rjm[:, 0, :]) and torch.equal(jv, rjv[:, 0, :])
+        assert torch.equal(torch.ops.mcpilco.gp_nlml(t, X, y), ops.gp_nlml(sp, X, y))
