@@ -124,4 +124,18 @@ def ur5_full(N=96, M=24, H=6, nb=40, seed=0):
     return sc
 
 
+def headline(N=8192, M=256, H=3, nb=50, seed=0):
+    """The bench workload's shape family (BASELINE.json configs[1]: cart-pole, SE + MPK(2) kernels, E = 2, D = 6) at its FULL training
+    size with few particles and a short horizon, so that the CPU oracle finishes in seconds.  No golden file: checked against the oracle."""
+    rs = np.random.RandomState(3000 + seed)
+    sc = scenario("c1", seed)
+    X, Y = _cartpole_like_data(rs, N, 0.1)
+    for g in sc["gps"]:
+        g["sigma_n"] = 0.1
+    sc.update(name="headline", N=N, M=M, H=H, X=X, Y=Y, policy=_policy_angles(rs, nb, 10.0))
+    sc["eps0"] = rs.randn(M, 4); sc["eps"] = rs.randn(H - 1, M, 2)
+    sc["masks"] = (rs.rand(H, M, nb) >= sc["p_dropout"]).astype(np.float64)
+    return sc
+
+
 ALL = ("c1", "c2", "c3", "c4", "delta")
