@@ -24,9 +24,10 @@ int dgemm_nt(int M, int N, int K, double alpha, const double* A, int lda, const 
   if (M <= 0 || N <= 0) return MCP_OK;
   MCP_CHECK_ARG((lda % 2 == 0) && (ldb % 2 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0),
                 "dgemm_nt: operands must be 16-byte aligned with even leading dimensions (lda=%d ldb=%d)", lda, ldb);
-  if ((size_t)M * N >= (size_t)512 * 512 && N >= 128) return launch<128, 128, 4, 2>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
-  // small products (the real MC-PILCO shapes: M = 200..400 particles, N = 60..400 points): 32 x 32 tiles spread the work
-  // over ~100 SMs instead of a dozen; one CTA's time per k-step is fixed by its SM's FP64 rate
+  // 128 x 128 tiles once there are enough of them to occupy most of the 148 SMs; below that 64 x 64 tiles (three CTAs per SM), and
+  // for the small products of the real MC-PILCO shapes (M = 200..400 particles, N = 60..400 points) 32 x 32 tiles, which spread the
+  // work over ~100 SMs instead of a dozen: one CTA's time per k-step is fixed by its SM's FP64 rate
+  if (N >= 128 && (size_t)cdiv(M, 128) * cdiv(N, 128) >= 120) return launch<128, 128, 4, 2>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
   if ((size_t)cdiv(M, 64) * cdiv(N, 64) < 96) return launch<32, 32, 2, 2>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
   return launch<64, 64, 2, 2>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
 }

@@ -139,5 +139,8 @@ int dgemm_nt(int M, int N, int K, double alpha, const double* A, int lda, const 
 // TMA + mbarrier pipelined variant for full (non-triangular) products (mcp_dgemm_tma.cu)
 bool dgemm_tma_usable(const double* A, int lda, const double* B, int ldb, const double* C, int ldc);
 int dgemm_nt_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc, cudaStream_t st);
+// the same pipeline with beta, the lower-tile mask and the contraction-range flags (the precompute's large triangular products)
+int dgemm_nt_tma_trim(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc,
+                      int tri, int kflags, cudaStream_t st);
 
 }  // namespace mcp

@@ -59,9 +59,12 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
                : "memory");
 }
 
+// TRIM = false: the posterior contraction (full product, C = alpha A B^T).  TRIM = true: the precompute's triangular products
+// (C = alpha A B^T + beta C with the lower-tile mask `tri` and the contraction-range flags `kflags` of mcp_dgemm.cuh).
+template <bool TRIM>
 __global__ void __launch_bounds__(T_THREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, double alpha,
-                 double* __restrict__ C, int ldc) {
+                 double* __restrict__ C, int ldc, double beta, int tri, int kflags) {
   extern __shared__ unsigned char smem_raw[];
   const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte aligned tiles
   const unsigned char* tiles = smem_raw + (base - smem_u32(smem_raw));  // same address for ordinary (compiler-scheduled) loads
@@ -73,7 +76,16 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int per_group = T_GROUP * tiles_n, group = blockIdx.x / per_group, first_m = group * T_GROUP;
   const int rows_here = min(tiles_m - first_m, T_GROUP), in_group = blockIdx.x - group * per_group;
   const int m0 = (first_m + in_group % rows_here) * T_BM, n0 = (in_group / rows_here) * T_BN;
-  const int KT = (K + T_BK - 1) / T_BK;
+  int kb = 0, ke = K;
+  if (TRIM) {
+    if (tri == 1 && n0 > m0 + T_BM - 1) return;
+    if (kflags & KF_A_UPPER) kb = max(kb, m0);
+    if (kflags & KF_B_UPPER) kb = max(kb, n0);
+    if (kflags & KF_A_LOWER) ke = min(ke, m0 + T_BM);
+    if (kflags & KF_B_LOWER) ke = min(ke, n0 + T_BN);
+    kb = (kb / T_BK) * T_BK;
+  }
+  const int KT = ke > kb ? (ke - kb + T_BK - 1) / T_BK : 0;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -91,8 +103,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (kn >= T_STAGES) mbar_wait(bars + 8 * (T_STAGES + s), ((kn / T_STAGES) - 1) & 1);
     const unsigned full = bars + 8 * s, dst = base + s * T_STAGE_BYTES;
     mbar_expect_tx(full, T_STAGE_BYTES);
-    tma_load_2d(dst, &tmA, kn * T_BK, m0, full);
-    tma_load_2d(dst + T_TILE_BYTES, &tmB, kn * T_BK, n0, full);
+    tma_load_2d(dst, &tmA, kb + kn * T_BK, m0, full);
+    tma_load_2d(dst + T_TILE_BYTES, &tmB, kb + kn * T_BK, n0, full);
   };
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -148,8 +160,14 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int jp = 0; jp < NJ / 2; jp++) {
       const int c = n0 + wn0 + 16 * jp + 4 * q;
       double* p = C + (size_t)r * ldc + c;
-      const double v0 = alpha * acc[i][2 * jp][0], v1 = alpha * acc[i][2 * jp + 1][0];
-      const double v2 = alpha * acc[i][2 * jp][1], v3 = alpha * acc[i][2 * jp + 1][1];
+      double v0 = alpha * acc[i][2 * jp][0], v1 = alpha * acc[i][2 * jp + 1][0];
+      double v2 = alpha * acc[i][2 * jp][1], v3 = alpha * acc[i][2 * jp + 1][1];
+      if (TRIM && beta != 0.0) {
+        if (c < N) v0 = fma(beta, p[0], v0);
+        if (c + 1 < N) v1 = fma(beta, p[1], v1);
+        if (c + 2 < N) v2 = fma(beta, p[2], v2);
+        if (c + 3 < N) v3 = fma(beta, p[3], v3);
+      }
       if (c + 3 < N) {
         *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
         *reinterpret_cast<double2*>(p + 2) = make_double2(v2, v3);
@@ -157,6 +175,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (c < N) p[0] = v0;
         if (c + 1 < N) p[1] = v1;
         if (c + 2 < N) p[2] = v2;
+        if (c + 3 < N) p[3] = v3;
       }
     }
   }
@@ -205,21 +224,34 @@ bool dgemm_tma_usable(const double* A, int lda, const double* B, int ldb, const 
          encode_fn() != nullptr;
 }
 
-int dgemm_nt_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc, cudaStream_t st) {
-  if (M <= 0 || N <= 0) return MCP_OK;
-  MCP_CHECK_ARG(dgemm_tma_usable(A, lda, B, ldb, C, ldc), "dgemm_nt_tma: operands must be 16-byte aligned with even leading dimensions");
+template <bool TRIM>
+static int launch_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc,
+                      int tri, int kflags, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    MCP_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
+    MCP_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
     configured = true;
   }
   CUtensorMap tmA, tmB;
   if (int e = make_map(&tmA, A, M, K, lda)) return e;
   if (int e = make_map(&tmB, B, N, K, ldb)) return e;
   dim3 grid((unsigned)cdiv(N, T_BN) * (unsigned)cdiv(M, T_BM));
-  dgemm_tma_kernel<<<grid, T_THREADS, T_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, alpha, C, ldc);
+  dgemm_tma_kernel<TRIM><<<grid, T_THREADS, T_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, alpha, C, ldc, beta, tri, kflags);
   MCP_LAUNCH_CHECK();
   return MCP_OK;
+}
+
+int dgemm_nt_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return MCP_OK;
+  MCP_CHECK_ARG(dgemm_tma_usable(A, lda, B, ldb, C, ldc), "dgemm_nt_tma: operands must be 16-byte aligned with even leading dimensions");
+  return launch_tma<false>(M, N, K, alpha, A, lda, B, ldb, 0.0, C, ldc, 0, 0, st);
+}
+
+int dgemm_nt_tma_trim(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc,
+                      int tri, int kflags, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return MCP_OK;
+  MCP_CHECK_ARG(dgemm_tma_usable(A, lda, B, ldb, C, ldc), "dgemm_nt_tma_trim: operands must be 16-byte aligned with even leading dimensions");
+  return launch_tma<true>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
 }
 
 }  // namespace mcp

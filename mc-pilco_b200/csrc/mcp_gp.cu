@@ -151,51 +151,81 @@ static int check_spec(const McpGpSpec* s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// precompute: blocked right-looking Cholesky (NB = 64) + blocked triangular inverse
+// precompute: recursive blocked Cholesky (64 x 64 leaves) with the triangular inverse carried along
 // ------------------------------------------------------------------------------------------------
 constexpr int NB = 64;
 
-// Factor one 64x64 diagonal block in place (lower), and write inv(L_kk) (lower, dense 64x64) to `invL`.
-// Non-SPD input yields NaN (sqrt of a negative pivot) which propagates, like every numerical failure here.
-__global__ void __launch_bounds__(256) potrf_block_kernel(double* __restrict__ Akk, int lda, double* __restrict__ invL) {
-  __shared__ double s[NB][NB + 1];
-  const int tid = threadIdx.x;
+// Factor one 64x64 diagonal block in place (lower), write inv(L_kk) (lower, dense 64x64) to `invL` and its transpose to `invLt`
+// (both with leading dimension ldi).  Non-SPD input yields NaN (sqrt of a negative pivot) which propagates, like every
+// numerical failure here.  Four threads per row (left-looking Cholesky: the dot product of a column step is split four ways
+// and combined by shuffles) and four threads per column of the inverse (forward substitution), everything in shared memory.
+constexpr int POTRF_SMEM = 2 * NB * (NB + 1) * (int)sizeof(double);
+__global__ void __launch_bounds__(256) potrf_block_kernel(double* __restrict__ Akk, int lda, double* __restrict__ invL,
+                                                          double* __restrict__ invLt, int ldi) {
+  extern __shared__ __align__(16) double potrf_smem[];
+  double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
+  double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem + NB * (NB + 1));
+  const int tid = threadIdx.x, i = tid >> 2, p = tid & 3;
   for (int e = tid; e < NB * NB; e += 256) s[e / NB][e % NB] = Akk[(size_t)(e / NB) * lda + (e % NB)];
   __syncthreads();
+  __shared__ double rdiag[NB];  // 1 / l_jj: one division per column on the critical path instead of one per row
   for (int j = 0; j < NB; j++) {
-    if (tid == 0) s[j][j] = sqrt(s[j][j]);
-    __syncthreads();
-    if (tid > j && tid < NB) s[tid][j] /= s[j][j];
-    __syncthreads();
-    // trailing update of the lower triangle: s[i][k] -= s[i][j] * s[k][j], j < k <= i
-    int rem = NB - 1 - j;
-    for (int e = tid; e < rem * rem; e += 256) {
-      int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) s[i][k] -= s[i][j] * s[k][j];
+    // row i, column j:  a_ij - sum_{k<j} l_ik l_jk   (rows above the diagonal idle); two independent chains per thread
+    double d0 = 0.0, d1 = 0.0;
+    if (i >= j) {
+      int k = p;
+      for (; k + 4 < j; k += 8) { d0 = fma(s[i][k], s[j][k], d0); d1 = fma(s[i][k + 4], s[j][k + 4], d1); }
+      if (k < j) d0 = fma(s[i][k], s[j][k], d0);
     }
+    double dot = d0 + d1;
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    if (i == j && p == 0) {
+      const double d = sqrt(s[j][j] - dot);
+      s[j][j] = d;
+      rdiag[j] = 1.0 / d;
+    }
+    __syncthreads();
+    if (i > j && p == 0) s[i][j] = (s[i][j] - dot) * rdiag[j];
     __syncthreads();
   }
   for (int e = tid; e < NB * NB; e += 256) {
-    int i = e / NB, k = e % NB;
-    Akk[(size_t)i * lda + k] = (k <= i) ? s[i][k] : 0.0;
+    int r = e / NB, k = e % NB;
+    Akk[(size_t)r * lda + k] = (k <= r) ? s[r][k] : 0.0;
   }
-  // inverse by forward substitution, one column per thread (each thread re-reads only its own writes)
-  if (tid < NB) {
-    const int c = tid;
-    for (int i = 0; i < NB; i++) {
-      double acc = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; k++) acc -= s[i][k] * invL[k * NB + c];
-      invL[i * NB + c] = (i < c) ? 0.0 : acc / s[i][i];
+  // inverse: column c = i of X = L^-1 by forward substitution,  x_rc = (delta_rc - sum_{c<=k<r} l_rk x_kc) / l_rr
+  {
+    const int c = i;
+    for (int r = 0; r < NB; r++) {
+      double a0 = 0.0, a1 = 0.0;
+      int k = c + p;
+      for (; k + 4 < r; k += 8) { a0 = fma(s[r][k], x[k][c], a0); a1 = fma(s[r][k + 4], x[k + 4][c], a1); }
+      if (k < r) a0 = fma(s[r][k], x[k][c], a0);
+      double acc = a0 + a1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (p == 0) x[r][c] = (r < c) ? 0.0 : ((r == c ? 1.0 : 0.0) - acc) * rdiag[r];
+      __syncwarp();
     }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    int r = e / NB, k = e % NB;
+    invL[(size_t)r * ldi + k] = x[r][k];
+    invLt[(size_t)r * ldi + k] = x[k][r];
   }
 }
 
-// dst[i][j] = src[j][i] for a 64x64 block
-__global__ void transpose_block_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd) {
-  __shared__ double t[NB][NB + 1];
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) t[e / NB][e % NB] = src[(size_t)(e / NB) * lds + e % NB];
+// dst[j][i] = src[i][j] for a rows x cols block (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd,
+                                                        int rows, int cols) {
+  __shared__ double t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (r0 + r < rows && c0 + tx < cols) t[r][tx] = src[(size_t)(r0 + r) * lds + c0 + tx];
   __syncthreads();
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(size_t)(e / NB) * ldd + e % NB] = t[e % NB][e / NB];
+  for (int c = ty; c < 32; c += 8)
+    if (c0 + c < cols && r0 + tx < rows) dst[(size_t)(c0 + c) * ldd + r0 + tx] = t[tx][c];
 }
 
 __global__ void pad_identity_kernel(double* K, int ld, int n, int np) {
@@ -237,7 +267,7 @@ using namespace mcp;
 
 extern "C" __attribute__((visibility("default"))) size_t mcpilco_gp_precompute_workspace_bytes(int N) {
   size_t np = align_up((size_t)(N > 0 ? N : 1), NB);
-  return (2 * np * np + np * NB + (np / NB) * NB * NB) * sizeof(double) + 256;
+  return 3 * np * np * sizeof(double) + 256;
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_gp_covariance(const McpGpSpec* spec, const double* X1, int n1, const double* X2, int n2, int add_noise,
@@ -266,48 +296,64 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_gp_precompute(cons
   cudaStream_t st = (cudaStream_t)stream;
   const int np = (int)align_up((size_t)N, NB), nblk = np / NB;
   double* Kp = (double*)align_up((size_t)workspace, 256);
-  double* W = Kp + (size_t)np * np;
-  double* P = W + (size_t)np * np;
-  double* invL = P + (size_t)np * NB;
+  double* I = Kp + (size_t)np * np;  // L^-1 (lower)
+  double* W = I + (size_t)np * np;   // L^-T (upper) = I^T
 
   // 1. K = k(X,X) + sigma_n2 I, padded to a multiple of the block size with an identity tail
-  MCP_CUDA(cudaMemsetAsync(Kp, 0, sizeof(double) * (size_t)np * np, st));
+  MCP_CUDA(cudaMemsetAsync(Kp, 0, sizeof(double) * 3 * (size_t)np * np, st));
   if (int e = launch_cov(*spec, Xtr, N, Xtr, N, 1, Kp, np, N, st)) return e;
   if (np > N) { pad_identity_kernel<<<cdiv(np - N, 128), 128, 0, st>>>(Kp, np, N, np); MCP_LAUNCH_CHECK(); }
 
-  // 2. right-looking blocked Cholesky: factor diagonal block, L21 = A21 inv(L11)^T, A22 -= L21 L21^T
-  for (int kb = 0; kb < nblk; kb++) {
-    double* Akk = Kp + (size_t)kb * NB * np + kb * NB;
-    potrf_block_kernel<<<1, 256, 0, st>>>(Akk, np, invL + (size_t)kb * NB * NB);
-    MCP_LAUNCH_CHECK();
-    int m = np - (kb + 1) * NB;
-    if (m > 0) {
-      double* A21 = Akk + (size_t)NB * np;
-      if (int e = dgemm_nt(m, NB, NB, 1.0, A21, np, invL + (size_t)kb * NB * NB, NB, 0.0, P, NB, 0, 0, st)) return e;
-      copy2d_kernel<<<dim3(cdiv(NB, 32), cdiv(m, 8)), dim3(32, 8), 0, st>>>(P, NB, A21, np, m, NB);
-      MCP_LAUNCH_CHECK();
-      if (int e = dgemm_nt(m, m, NB, -1.0, P, NB, P, NB, 1.0, A21 + NB, np, 1, 0, st)) return e;
+  // 2 + 3. recursive Cholesky with the triangular inverse carried along, so that every update is a large NT product:
+  //   [A11 .; A21 A22]:  (L11, I11) <- node(A11);  L21 = A21 I11^T;  A22 -= L21 L21^T;  (L22, I22) <- node(A22);
+  //   I21 = -I22 (L21 I11),  formed as  T^T = I11^T L21^T  (scratch: the unused upper-right block of Kp)  and  I21 = -I22 (T^T)^T.
+  // Leaves are 64 x 64 blocks factored and inverted by one CTA.  L overwrites the lower triangle of Kp.
+  struct Rec {
+    double *Kp, *I, *W; int np; cudaStream_t st;
+    static int gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc,
+                    int tri, int kflags, cudaStream_t st) {
+      if ((size_t)cdiv(M, 128) * cdiv(N, 128) >= 120 && dgemm_tma_usable(A, lda, B, ldb, C, ldc))
+        return dgemm_nt_tma_trim(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
+      return dgemm_nt(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags, st);
     }
+    int node(int b0, int nb) const {
+      const size_t o = (size_t)b0 * NB * np + (size_t)b0 * NB;   // offset of the node's diagonal origin
+      if (nb == 1) {
+        potrf_block_kernel<<<1, 256, POTRF_SMEM, st>>>(Kp + o, np, I + o, W + o, np);
+        MCP_LAUNCH_CHECK();
+        return MCP_OK;
+      }
+      const int nb1 = nb / 2, nb2 = nb - nb1, h1 = nb1 * NB, h2 = nb2 * NB;
+      if (int e = node(b0, nb1)) return e;
+      double* A21 = Kp + o + (size_t)h1 * np;      // [h2 x h1]
+      double* A22 = A21 + h1;                      // [h2 x h2]
+      double* U12 = Kp + o + h1;                   // [h1 x h2] scratch (stale upper triangle)
+      double* I21 = I + o + (size_t)h1 * np;       // [h2 x h1]
+      if (int e = gemm(h2, h1, h1, 1.0, A21, np, I + o, np, 0.0, I21, np, 0, KF_B_LOWER, st)) return e;
+      copy2d_kernel<<<dim3(cdiv(h1, 32), cdiv(h2, 8)), dim3(32, 8), 0, st>>>(I21, np, A21, np, h2, h1);
+      MCP_LAUNCH_CHECK();
+      if (int e = gemm(h2, h2, h1, -1.0, A21, np, A21, np, 1.0, A22, np, 1, 0, st)) return e;
+      if (int e = node(b0 + nb1, nb2)) return e;
+      if (int e = gemm(h1, h2, h1, 1.0, W + o, np, A21, np, 0.0, U12, np, 0, KF_A_UPPER, st)) return e;
+      if (int e = gemm(h2, h1, h2, -1.0, I + o + (size_t)h1 * np + h1, np, U12, np, 0.0, I21, np, 0, KF_A_LOWER, st)) return e;
+      transpose_kernel<<<dim3(cdiv(h1, 32), cdiv(h2, 32)), 256, 0, st>>>(I21, np, W + o + h1, np, h2, h1);
+      MCP_LAUNCH_CHECK();
+      return MCP_OK;
+    }
+  };
+  static bool potrf_configured = false;
+  if (!potrf_configured) {
+    MCP_CUDA(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    potrf_configured = true;
   }
-  if (Lfac) {  // export L (lower; upper part of Kp still holds stale K entries, mask them)
+  if (int e = Rec{Kp, I, W, np, st}.node(0, nblk)) return e;
+  if (Lfac) {  // export L (lower; the upper part of Kp holds scratch, mask it)
     lower_copy_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Lfac, ld, N);
     MCP_LAUNCH_CHECK();
   }
 
-  // 3. W = L^-T (upper), block column by block column:  W_ji = -(sum_k W_jk L_ik^T) inv(L_ii)^T,  W_ii = inv(L_ii)^T
-  MCP_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np, st));
-  for (int i = 0; i < nblk; i++) {
-    transpose_block_kernel<<<1, 256, 0, st>>>(invL + (size_t)i * NB * NB, NB, W + (size_t)i * NB * np + i * NB, np);
-    MCP_LAUNCH_CHECK();
-    if (i > 0) {
-      int mi = i * NB;
-      if (int e = dgemm_nt(mi, NB, mi, 1.0, W, np, Kp + (size_t)i * NB * np, np, 0.0, P, NB, 0, KF_A_UPPER, st)) return e;
-      if (int e = dgemm_nt(mi, NB, NB, -1.0, P, NB, invL + (size_t)i * NB * NB, NB, 0.0, W + i * NB, np, 0, 0, st)) return e;
-    }
-  }
-
   // 4. K^-1 = W W^T (lower tiles, contraction trimmed to k >= max(row blocks)), mirrored into the output
-  if (int e = dgemm_nt(np, np, np, 1.0, W, np, W, np, 0.0, Kp, np, 1, KF_A_UPPER | KF_B_UPPER, st)) return e;
+  if (int e = Rec::gemm(np, np, np, 1.0, W, np, W, np, 0.0, Kp, np, 1, KF_A_UPPER | KF_B_UPPER, st)) return e;
   symmetrize_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Kinv, ld, N);
   MCP_LAUNCH_CHECK();
   if (ld > N) {  // keep the row padding finite (zero) for the tile loaders
