@@ -2,7 +2,10 @@
 // triangular inverse, K^-1, alpha) and the posterior mean/variance with their input Jacobians.
 // Reference behaviour being reproduced: gpr_lib/GP_prior/GP_prior.py:91-155 and the kernel classes
 // cited in mcp_kfn.cuh; driven by model_learning/Model_learning.py:163-208,265-336.
+#include <cooperative_groups.h>
+
 #include "mcp_dgemm.cuh"
+#include "mcp_gpdev.cuh"
 #include "mcp_kfn.cuh"
 
 namespace mcp {
@@ -13,9 +16,8 @@ namespace mcp {
 // K[i][j] = k(X1_i, X2_j) for i < n1, j < n2; columns n2..ncols_out-1 are written as zero (row padding for
 // the 16-byte tile loads of the GEMM).  add_noise adds sigma_n2 on the diagonal (X2 == X1 case).
 template <int DT>
-__global__ void __launch_bounds__(256) cov_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X1, int n1,
-                                                  const double* __restrict__ X2, int n2, int add_noise, double* __restrict__ K,
-                                                  int ldk, int ncols_out) {
+__device__ __forceinline__ void cov_body(const McpGpSpec& s, const double* __restrict__ X1, int n1, const double* __restrict__ X2, int n2,
+                                         int add_noise, double* __restrict__ K, int ldk, int ncols_out) {
   int j = blockIdx.x * 32 + (threadIdx.x & 31);
   int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
   if (j >= ncols_out) return;
@@ -36,6 +38,85 @@ __global__ void __launch_bounds__(256) cov_kernel(const __grid_constant__ McpGpS
   }
 }
 
+template <int DT>
+__global__ void __launch_bounds__(256) cov_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X1, int n1,
+                                                  const double* __restrict__ X2, int n2, int add_noise, double* __restrict__ K,
+                                                  int ldk, int ncols_out) {
+  cov_body<DT>(s, X1, n1, X2, n2, add_noise, K, ldk, ncols_out);
+}
+
+// K* tiles for WIDE gp inputs (8 < D <= 32: SE + at most one linear term, the UR5 model).  The generic kernel keeps x[DT], y[DT] in
+// registers and walks the whole McpGpSpec per entry (~100 loads); here one thread owns a training point (column), the block a strip of
+// 16 particles: the training tile is staged coalesced, the particle rows as (x, w1 x) pairs read by broadcast, and the loop runs
+// dimension-outer over 16 row accumulators.  Arithmetic per entry is exactly KFn::k's, so the result is bit-identical to cov_kernel.
+constexpr int CW_THREADS = 128, CW_ROWS = 16;
+static bool wide_reduce_ok(const McpGpSpec& s);
+template <int DT>
+__device__ __forceinline__ void cov_wide_body(const McpGpSpec& s, const double* __restrict__ X1, int n1, const double* __restrict__ X2, int n2,
+                                              double* __restrict__ K, int ldk, int ncols_out) {
+  __shared__ double sy[CW_THREADS][DT + 1];
+  __shared__ double2 sxp[CW_ROWS][DT];
+  __shared__ double sil[DT];
+  const int D = s.D, tid = threadIdx.x, nb0 = blockIdx.x * CW_THREADS, n = nb0 + tid, i0 = blockIdx.y * CW_ROWS;
+  const bool np1 = s.n_poly == 1;
+  const int cnt = min(CW_THREADS, n2 - nb0);
+  for (int el = tid; el < cnt * D; el += CW_THREADS) {
+    const int r = el / D, j = el - r * D;
+    sy[r][j] = X2[(size_t)nb0 * D + el];
+  }
+  for (int el = tid; el < CW_ROWS * DT; el += CW_THREADS) {
+    const int r = el / DT, j = el - r * DT;
+    const double x = (i0 + r < n1 && j < D) ? X1[(size_t)(i0 + r) * D + j] : 0.0;
+    const double w = (np1 && j < D) ? s.poly_w2[0][0][j] : 0.0;
+    sxp[r][j] = make_double2(x, w * x);
+  }
+  if (tid < DT) sil[tid] = tid < D ? s.inv_ls[tid] : 0.0;
+  __syncthreads();
+  if (n >= ncols_out) return;
+  double d2[CW_ROWS], a[CW_ROWS];
+  const double off = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0;
+#pragma unroll
+  for (int r = 0; r < CW_ROWS; r++) { d2[r] = 0.0; a[r] = off; }
+  if (n < n2) {
+    for (int j = 0; j < D; j++) {
+      const double y = sy[tid][j], il = sil[j];
+#pragma unroll
+      for (int r = 0; r < CW_ROWS; r++) {
+        const double2 xp = sxp[r][j];
+        const double t = (xp.x - y) * il;
+        d2[r] = fma(t, t, d2[r]);
+        a[r] = fma(xp.y, y, a[r]);
+      }
+    }
+  }
+  const double lam = s.lambda;
+  const bool se = s.has_se != 0;
+#pragma unroll
+  for (int r = 0; r < CW_ROWS; r++) {
+    const int i = i0 + r;
+    if (i >= n1) break;
+    double kv = 0.0;
+    if (n < n2) {
+      if (se) kv = lam * exp(-d2[r]);
+      if (np1) kv += a[r];
+    }
+    K[(size_t)i * ldk + n] = kv;
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(CW_THREADS) cov_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X1, int n1,
+                                                              const double* __restrict__ X2, int n2, double* __restrict__ K, int ldk,
+                                                              int ncols_out) {
+  cov_wide_body<DT>(s, X1, n1, X2, n2, K, ldk, ncols_out);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(CW_THREADS) cov_wide_batched_kernel(const McpGpDev* __restrict__ gps, const double* __restrict__ Xs, int M,
+                                                                      double* __restrict__ Ks, int ldk, size_t gp_stride) {
+  const McpGpDev& g = gps[blockIdx.z];
+  cov_wide_body<DT>(g.spec, Xs, M, g.Xtr, g.N, Ks + blockIdx.z * gp_stride, ldk, ldk);
+}
 
 // K* tile kernel for the same kernel shapes as the fast reduce (SE + Volterra polynomial, D <= 8): one thread per training
 // point (its inputs, pre-scaled, stay in registers), 64 particles per block staged in shared memory with their
@@ -131,6 +212,14 @@ static int launch_cov(const McpGpSpec& s, const double* X1, int n1, const double
     else if (s.D <= 6) { if (np_ == 0) MCP_FAST_COV(6, 0); else if (np_ == 1) MCP_FAST_COV(6, 1); else MCP_FAST_COV(6, 2); }
     else { if (np_ == 0) MCP_FAST_COV(8, 0); else MCP_FAST_COV(8, 1); }
 #undef MCP_FAST_COV
+    MCP_LAUNCH_CHECK();
+    return MCP_OK;
+  }
+  if (!add_noise && wide_reduce_ok(s)) {  // wide inputs (UR5): same values as cov_kernel, an order of magnitude fewer loads
+    dim3 gridw(cdiv(ncols_out, CW_THREADS), cdiv(n1, CW_ROWS));
+    if (s.D <= 16) cov_wide_kernel<16><<<gridw, CW_THREADS, 0, st>>>(s, X1, n1, X2, n2, K, ldk, ncols_out);
+    else if (s.D <= 24) cov_wide_kernel<24><<<gridw, CW_THREADS, 0, st>>>(s, X1, n1, X2, n2, K, ldk, ncols_out);
+    else cov_wide_kernel<32><<<gridw, CW_THREADS, 0, st>>>(s, X1, n1, X2, n2, K, ldk, ncols_out);
     MCP_LAUNCH_CHECK();
     return MCP_OK;
   }
@@ -608,79 +697,111 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
 // Reduce for WIDE gp inputs (8 < D <= 32; the UR5 model has D = 24) with an SE term and at most one linear term: a lane cannot
 // hold 4 D accumulators, so the gradient sums are done in two stages per tile of 64 training points.  Stage 1, lanes over points:
 // kernel value, mean / q / E0 accumulators and the four per-point coefficients T[n] = (a e, v e, a, v) into shared memory.
-// Stage 2, lanes over (dimension j, channel c) pairs: acc[j][c] += Y[n][j] T[n][c] — no cross-lane reduction at all.
+// Stage 2, lane j over its dimension and all four channels: acc[j][c] += Y[n][j] T[n][c] — no cross-lane reduction at all.
 //   sum_n a_n dk_n/dx_j = -2 ils_j^2 (x_j E0 - acc[j][a e]) + w1_j acc[j][a]        (and the same with v for the variance)
+// One warp per particle gives only E * M warps (1200 for UR5: 8 per SM, latency-bound at 67 us per step), so the training points are
+// split over the CTAs of a thread-block cluster (gridDim.z = cluster size = 1, 2 or 4, chosen from N alone): each CTA reduces every
+// nseg-th tile, the partial sums meet in rank 0 through distributed shared memory in a fixed order (bit-stable), rank 0 finalises.
 constexpr int WIDE_TILE = 64;
-__global__ void __launch_bounds__(256) posterior_reduce_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
-                                                                    int M, const double* __restrict__ Xtr,
-                                                                    const double* __restrict__ alpha, int N,
-                                                                    const double* __restrict__ V, int ldv, double var_scale, int E,
-                                                                    int e, double* __restrict__ mean, double* __restrict__ var,
-                                                                    double* __restrict__ jmean, double* __restrict__ jvar) {
+static inline int wide_segments(int N) {
+  const int tiles = cdiv(N, WIDE_TILE);
+  return tiles >= 4 ? 4 : (tiles >= 2 ? 2 : 1);
+}
+__device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const double* __restrict__ Xs, int M, const double* __restrict__ Xtr,
+                                                 const double* __restrict__ alpha, int N, const double* __restrict__ V, int ldv,
+                                                 double var_scale, int E, int e, double* __restrict__ mean, double* __restrict__ var,
+                                                 double* __restrict__ jmean, double* __restrict__ jvar) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nseg = (int)cluster.num_blocks(), seg = (int)cluster.block_rank();
   __shared__ double sY[WIDE_TILE][MCP_MAX_D + 1];  // +1: lanes over points read a column without bank conflicts
   __shared__ double sA[WIDE_TILE];
-  __shared__ double sT[8][WIDE_TILE][4];
-  __shared__ double sX[8][MCP_MAX_D];
-  __shared__ double sG[8][MCP_MAX_D][4];
+  __shared__ __align__(32) double sT[8][WIDE_TILE][4];
+  __shared__ double sX[8][MCP_MAX_D], sXw[8][MCP_MAX_D];
+  __shared__ double sIl[MCP_MAX_D];
+  __shared__ __align__(32) double sG[8][MCP_MAX_D][4];
+  __shared__ double sS[8][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int m = min(blockIdx.x * 8 + warp, M - 1);
   const bool owner = blockIdx.x * 8 + warp < M;
   const int D = s.D, np1 = s.n_poly;  // np1 in {0, 1}
-  if (lane < D) sX[warp][lane] = Xs[(size_t)m * D + lane];
-  __syncwarp();
+  const double off = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0, lam = s.lambda;
+  const bool se = s.has_se != 0;
+  if (lane < D) {
+    const double xj = Xs[(size_t)m * D + lane];
+    sX[warp][lane] = xj;
+    sXw[warp][lane] = np1 ? s.poly_w2[0][0][lane] * xj : 0.0;
+  }
+  if (tid < MCP_MAX_D) sIl[tid] = tid < D ? s.inv_ls[tid] : 0.0;
   double mu = 0.0, q = 0.0, E0a = 0.0, E0v = 0.0;
-  // stage-2 ownership: pair p = lane + 32 r  ->  (j = p / 4, c = p % 4), r < 4 covers D <= 32
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // lane j < D: channels (a e, v e, a, v) of dimension j
   const double* v = V + (size_t)m * ldv;
-  for (int n0 = 0; n0 < N; n0 += WIDE_TILE) {
-    __syncthreads();  // previous tile fully consumed
+  for (int n0 = seg * WIDE_TILE; n0 < N; n0 += nseg * WIDE_TILE) {
+    __syncthreads();  // previous tile fully consumed (first pass: sX / sXw / sIl visible)
+    const int cnt = min(WIDE_TILE, N - n0);
     for (int el = tid; el < WIDE_TILE * D; el += 256) {
       const int i = el / D, j = el - i * D;
-      sY[i][j] = (n0 + i < N) ? Xtr[(size_t)(n0 + i) * D + j] : 0.0;
+      sY[i][j] = (i < cnt) ? Xtr[(size_t)n0 * D + el] : 0.0;
     }
-    if (tid < WIDE_TILE) sA[tid] = (n0 + tid < N) ? alpha[n0 + tid] : 0.0;
+    if (tid < WIDE_TILE) sA[tid] = (tid < cnt) ? alpha[n0 + tid] : 0.0;
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < WIDE_TILE / 32; h++) {
       const int i = h * 32 + lane, n = n0 + i;
-      double d2 = 0.0, L1 = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0;
+      double d2 = 0.0, L1 = off;
       for (int j = 0; j < D; j++) {
-        const double xj = sX[warp][j], yj = sY[i][j];
-        const double t = (xj - yj) * s.inv_ls[j];
+        const double yj = sY[i][j];
+        const double t = (sX[warp][j] - yj) * sIl[j];
         d2 = fma(t, t, d2);
-        if (np1) L1 = fma(s.poly_w2[0][0][j] * xj, yj, L1);
+        L1 = fma(sXw[warp][j], yj, L1);
       }
-      const double ev = s.has_se ? s.lambda * exp(-d2) : 0.0, kv = ev + L1;
+      const double ev = se ? lam * exp(-d2) : 0.0, kv = ev + (np1 ? L1 : 0.0);
       const double a = sA[i], vn = (n < N) ? v[n] : 0.0;
       mu = fma(a, kv, mu);
       q = fma(vn, kv, q);
       const double ta = a * ev, tv = vn * ev;
       E0a += ta;
       E0v += tv;
-      sT[warp][i][0] = ta; sT[warp][i][1] = tv; sT[warp][i][2] = a; sT[warp][i][3] = vn;
+      *reinterpret_cast<double4*>(&sT[warp][i][0]) = make_double4(ta, tv, a, vn);
     }
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int p = lane + 32 * r, j = p >> 2, c = p & 3;
-      if (j < D) {
-        double a2 = acc[r];
+    if (lane < D) {
 #pragma unroll 8
-        for (int i = 0; i < WIDE_TILE; i++) a2 = fma(sY[i][j], sT[warp][i][c], a2);
-        acc[r] = a2;
+      for (int i = 0; i < WIDE_TILE; i++) {
+        const double y = sY[i][lane];
+        const double4 t4 = *reinterpret_cast<const double4*>(&sT[warp][i][0]);
+        acc[0] = fma(y, t4.x, acc[0]);
+        acc[1] = fma(y, t4.y, acc[1]);
+        acc[2] = fma(y, t4.z, acc[2]);
+        acc[3] = fma(y, t4.w, acc[3]);
       }
     }
   }
   mu = warp_sum(mu); q = warp_sum(q); E0a = warp_sum(E0a); E0v = warp_sum(E0v);
+  if (lane == 0) { sS[warp][0] = mu; sS[warp][1] = q; sS[warp][2] = E0a; sS[warp][3] = E0v; }
+  if (lane < D) *reinterpret_cast<double4*>(&sG[warp][lane][0]) = make_double4(acc[0], acc[1], acc[2], acc[3]);
+  if (nseg > 1) {
+    cluster.sync();
+    if (seg == 0) {  // fixed order: own partial, then ranks 1, 2, 3
+      for (int r = 1; r < nseg; r++) {
+        const double* rG = cluster.map_shared_rank(&sG[0][0][0], r);
+        const double* rS = cluster.map_shared_rank(&sS[0][0], r);
+        if (lane < D) {
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const int p = lane + 32 * r, j = p >> 2, c = p & 3;
-    if (j < D) sG[warp][j][c] = acc[r];
+          for (int c = 0; c < 4; c++) sG[warp][lane][c] += rG[(warp * MCP_MAX_D + lane) * 4 + c];
+        }
+        if (lane < 4) sS[warp][lane] += rS[warp * 4 + lane];
+      }
+    }
+    cluster.sync();  // the other ranks' shared memory stays alive until rank 0 has read it
+    if (seg != 0) return;
   }
   __syncwarp();
+  E0a = sS[warp][2];
+  E0v = sS[warp][3];
   if (owner && lane < D) {
     const int j = lane;
-    const double il2 = -2.0 * s.inv_ls[j] * s.inv_ls[j], xj = sX[warp][j], w1 = np1 ? s.poly_w2[0][0][j] : 0.0;
+    const double il2 = -2.0 * sIl[j] * sIl[j], xj = sX[warp][j], w1 = np1 ? s.poly_w2[0][0][j] : 0.0;
     const double ga = il2 * (xj * E0a - sG[warp][j][0]) + w1 * sG[warp][j][2];
     const double gv = il2 * (xj * E0v - sG[warp][j][1]) + w1 * sG[warp][j][3];
     // d k(x,x) / dx_j for SE + linear: 2 w1_j x_j
@@ -689,15 +810,55 @@ __global__ void __launch_bounds__(256) posterior_reduce_wide_kernel(const __grid
     jvar[((size_t)m * E + e) * D + j] = var_scale * (dkd - 2.0 * gv);
   }
   if (owner && lane == 0) {
-    double kd = s.has_se ? s.lambda : 0.0;
+    double kd = se ? lam : 0.0;
     if (np1) {
-      double L = s.poly_w2[0][0][MCP_MAX_D];
+      double L = off;
       for (int j = 0; j < D; j++) L = fma(s.poly_w2[0][0][j] * sX[warp][j], sX[warp][j], L);
       kd += L;
     }
-    mean[(size_t)m * E + e] = s.mean0 + mu;
-    var[(size_t)m * E + e] = var_scale * (kd - q);
+    mean[(size_t)m * E + e] = s.mean0 + sS[warp][0];
+    var[(size_t)m * E + e] = var_scale * (kd - sS[warp][1]);
   }
+}
+
+__global__ void __launch_bounds__(256) posterior_reduce_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
+                                                                    int M, const double* __restrict__ Xtr,
+                                                                    const double* __restrict__ alpha, int N,
+                                                                    const double* __restrict__ V, int ldv, double var_scale, int E,
+                                                                    int e, double* __restrict__ mean, double* __restrict__ var,
+                                                                    double* __restrict__ jmean, double* __restrict__ jvar) {
+  reduce_wide_body(s, Xs, M, Xtr, alpha, N, V, ldv, var_scale, E, e, mean, var, jmean, jvar);
+}
+
+// the same reduce for ALL outputs in one launch (blockIdx.y = output); a link of a programmatic-dependent-launch chain
+__global__ void __launch_bounds__(256) posterior_reduce_wide_batched_kernel(const McpGpDev* __restrict__ gps, const double* __restrict__ Xs,
+                                                                            int M, const double* __restrict__ V, int ldv, size_t gp_stride,
+                                                                            int E, double* __restrict__ mean, double* __restrict__ var,
+                                                                            double* __restrict__ jmean, double* __restrict__ jvar) {
+  pdl_wait();
+  const int e = blockIdx.y;
+  const McpGpDev& g = gps[e];
+  reduce_wide_body(g.spec, Xs, M, g.Xtr, g.alpha, g.N, V + e * gp_stride, ldv, g.var_scale, E, e, mean, var, jmean, jvar);
+}
+
+// launch with a runtime cluster size along z (and, optionally, programmatic stream serialisation)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster_z(bool pdl, int nseg, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = (unsigned)nseg;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 static bool wide_reduce_ok(const McpGpSpec& s) {
@@ -710,6 +871,58 @@ static inline int ld16(int n) { return (n + 15) / 16 * 16; }
 size_t ozaki_scratch_bytes(int mc, int N, int S);
 int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t* Bplanes, const int32_t* Bexp, double* V, int ldv, void* scratch,
                    size_t scratch_bytes, cudaStream_t st);
+
+// ---- batched posterior: all E outputs of a step in three launches (K* rows, contraction, reduce) on one stream ----------------
+// For small rollouts with wide gp inputs (UR5: D = 24, E = 6, 200 particles) the per-output chains on side streams cost ~36 API calls
+// per step and the rollout was host-bound (135 us per step); batched over the output index it is 3 launches per step.  Same device
+// code as the per-output kernels, so the results are bit-identical.
+bool gp_posterior_batched_ok(const McpGp* gps, int E, bool jac) {
+  if (!jac || E < 2 || getenv("MCPILCO_NO_BATCHED_STEP") != nullptr) return false;
+  for (int e = 0; e < E; e++) {
+    const McpGp& g = gps[e];
+    if (!wide_reduce_ok(g.spec) || g.ozaki_slices != 0 || g.spec.D != gps[0].spec.D) return false;
+    if (wide_segments(g.N) != wide_segments(gps[0].N)) return false;  // one cluster size per launch, and the same split as the per-output path
+    if (g.N < 1 || !g.Xtr || !g.alpha || !g.Kinv || g.ld_kinv < g.N || g.ld_kinv % 2 != 0 || ((uintptr_t)g.Kinv % 16) != 0) return false;
+  }
+  return true;
+}
+
+size_t gp_posterior_batched_doubles(int M, int E, int nmax) {
+  return 2 * (size_t)E * M * ld16(nmax) + (sizeof(McpGpDev) * (size_t)E + 7) / 8 + 64;
+}
+
+// one-time setup per rollout: upload the table to the front of `scratch`; returns the device table and the K* / V base
+int gp_posterior_batched_setup(const McpGp* gps, int E, int M, int nmax, double* scratch, size_t scratch_doubles, const McpGpDev** tab_out,
+                               double** ks_out, cudaStream_t st) {
+  MCP_CHECK_ARG(scratch_doubles >= gp_posterior_batched_doubles(M, E, nmax), "rollout (batched step): workspace too small");
+  McpGpDev host_tab[MCP_MAX_E];
+  gpdev_fill(host_tab, gps, E);
+  McpGpDev* tab = reinterpret_cast<McpGpDev*>(scratch);
+  MCP_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(McpGpDev) * (size_t)E, cudaMemcpyHostToDevice, st));
+  double* Ks = scratch + (sizeof(McpGpDev) * (size_t)E + 7) / 8 + 8;
+  *ks_out = reinterpret_cast<double*>(align_up((size_t)Ks, 256));
+  *tab_out = tab;
+  return MCP_OK;
+}
+
+int gp_posterior_batched(const McpGpDev* tab, int E, int D, int nmax, const double* Xs, int M, double* mean, double* var, double* jmean,
+                         double* jvar, double* Ks, cudaStream_t st) {
+  const int ldk = ld16(nmax);
+  const size_t gp_stride = (size_t)M * ldk;
+  double* V = Ks + (size_t)E * gp_stride;
+  const bool pdl = pdl_enabled();
+  dim3 cgrid(cdiv(ldk, CW_THREADS), cdiv(M, CW_ROWS), E);
+  if (D <= 16) cov_wide_batched_kernel<16><<<cgrid, CW_THREADS, 0, st>>>(tab, Xs, M, Ks, ldk, gp_stride);
+  else if (D <= 24) cov_wide_batched_kernel<24><<<cgrid, CW_THREADS, 0, st>>>(tab, Xs, M, Ks, ldk, gp_stride);
+  else cov_wide_batched_kernel<32><<<cgrid, CW_THREADS, 0, st>>>(tab, Xs, M, Ks, ldk, gp_stride);
+  MCP_LAUNCH_CHECK();
+  if (int err = launch_small_gemm(tab, M, nmax, E, Ks, V, ldk, gp_stride, pdl, st)) return err;
+  const int nseg = wide_segments(nmax);  // gp_posterior_batched_ok: every output has this segment count
+  MCP_CUDA(launch_cluster_z(pdl, nseg, posterior_reduce_wide_batched_kernel, dim3(cdiv(M, 8), E, nseg), dim3(256), st, tab, Xs, M, V, ldk,
+                            gp_stride, E, mean, var, jmean, jvar));
+  count_launch();
+  return MCP_OK;
+}
 
 // posterior of ONE GP for a chunk of particles through scratch [2 x Mc x ld16(N)]
 int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, double* mean, double* var, double* jmean,
@@ -759,8 +972,9 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
       else { if (np_ == 0) MCP_FAST_REDUCE(8, 0); else if (np_ == 1) MCP_FAST_REDUCE(8, 1); else MCP_FAST_REDUCE(8, 2); }
 #undef MCP_FAST_REDUCE
     } else if (jac && wide_reduce_ok(g.spec)) {
-      posterior_reduce_wide_kernel<<<grid, 256, 0, st>>>(g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e,
-                                                         mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv);
+      const int nseg = wide_segments(N);
+      MCP_CUDA(launch_cluster_z(false, nseg, posterior_reduce_wide_kernel, dim3(cdiv(mc, 8), 1, nseg), dim3(256), st, g.spec, xs, mc, g.Xtr,
+                                g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv));
     } else if (jac) {
       MCP_DISPATCH_D(g.spec.D, (posterior_reduce_kernel<DT, true><<<grid, 256, 0, st>>>(
                                    g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E,

@@ -13,6 +13,13 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
 bool small_path_ok(const McpRollout* r);
 size_t small_path_doubles(int M, int E, int Nmax);
 int rollout_fwd_small(const McpRollout* r, double* Xs, double* nv, double* scratch, size_t scratch_doubles, cudaStream_t st);
+struct McpGpDev;
+bool gp_posterior_batched_ok(const McpGp* gps, int E, bool jac);
+size_t gp_posterior_batched_doubles(int M, int E, int nmax);
+int gp_posterior_batched_setup(const McpGp* gps, int E, int M, int nmax, double* scratch, size_t scratch_doubles, const McpGpDev** tab_out,
+                               double** ks_out, cudaStream_t st);
+int gp_posterior_batched(const McpGpDev* tab, int E, int D, int nmax, const double* Xs, int M, double* mean, double* var, double* jmean,
+                         double* jvar, double* Ks, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // forward kernels
@@ -40,6 +47,7 @@ __global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__
   for (int b = lane; b < pol.nb; b += 32) {
     const double* c = pol.centers + (size_t)b * pol.Dp;
     double d = 0.0;
+#pragma unroll 8
     for (int j = 0; j < pol.Dp; j++) {
       double r = (s_z[w][j] - c[j]) * s_il[j];
       d = fma(r, r, d);
@@ -99,6 +107,7 @@ __global__ void __launch_bounds__(128) policy_fwd_block_kernel(const __grid_cons
   for (int b = tid; b < pol.nb; b += 128) {
     const double* c = pol.centers + (size_t)b * pol.Dp;
     double d = 0.0;
+#pragma unroll 8
     for (int j = 0; j < pol.Dp; j++) {
       double r = (s_z[j] - c[j]) * s_il[j];
       d = fma(r, r, d);
@@ -737,6 +746,14 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   if (small) {
     if (int err = rollout_fwd_small(r, w.Xs, w.nv, w.scratch, w.scratch_doubles, st)) return err;
   }
+  // small rollouts with wide gp inputs: all outputs of a step batched into three launches instead of E chains on side streams
+  const bool batched = !small && fan != nullptr && gp_posterior_batched_ok(r->gps, E, r->need_grad != 0) &&
+                       w.scratch_doubles >= gp_posterior_batched_doubles(M, E, nmax);
+  const McpGpDev* tab = nullptr;
+  double* bKs = nullptr;
+  if (batched) {
+    if (int err = gp_posterior_batched_setup(r->gps, E, M, nmax, w.scratch, w.scratch_doubles, &tab, &bKs, st)) return err;
+  }
   for (int t = 0; t < H && !small; t++) {
     const double* x_t = r->states + (size_t)t * M * Ds;
     const double* p_t = meas ? r->pol_in + (size_t)t * M * Ds : x_t;
@@ -744,7 +761,9 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
                                 t < H - 1 ? w.Xs : nullptr, st))
       return err;
     if (t == H - 1) break;
-    if (fan != nullptr) {
+    if (batched) {
+      if (int err = gp_posterior_batched(tab, E, D, nmax, w.Xs, M, w.mean, w.var, w.jmean, w.jvar, bKs, st)) return err;
+    } else if (fan != nullptr) {
       // small problem: the E per-output chains (K* tile -> contraction -> reduce) are independent; run them side by side
       MCP_CUDA(cudaEventRecord(fan->fork, st));
       for (int e = 0; e < E; e++) {

@@ -393,6 +393,46 @@ def test_ur5_true_dimensions_vs_oracle(nh):
         assert relmax(jm[:, e, :], gm.numpy()) < 1e-6 and relmax(jv[:, e, :], gv.numpy()) < 1e-5
 
 
+def test_wide_covariance_kernel_is_bit_identical_to_generic(nh):
+    """Wide gp inputs (D = 24) take a dedicated K* kernel; the K + noise build of the precompute takes the generic one.  Same arithmetic
+    per entry: off the diagonal the two must agree bit for bit (and on it up to the added noise)."""
+    from mcpilco_b200 import _ops as ops
+    sc = scenarios.ur5_full()
+    X = nh.G(sc["X"])
+    for sp in nh.native_specs(sc):
+        Kw = ops.gp_covariance(sp, X, X)                       # cross-covariance path -> cov_wide_kernel
+        Kg = ops.gp_covariance(sp, X, None, add_noise=True)    # K + sigma_n^2 I    -> cov_kernel
+        off = ~torch.eye(X.shape[0], dtype=torch.bool, device=X.device)
+        assert torch.equal(Kw[off], Kg[off])
+        assert torch.allclose(torch.diagonal(Kg) - torch.diagonal(Kw), torch.full((X.shape[0],), sp.sigma_n2, dtype=torch.float64, device=X.device),
+                              rtol=0, atol=1e-15)
+        # ragged shapes: rows / columns that are not multiples of the strip sizes
+        Xa, Xb = X[:37], X[5:96]
+        Kr = ops.gp_covariance(sp, Xa, Xb)
+        assert torch.equal(Kr, Kw[:37, 5:96])
+
+
+def test_ur5_batched_step_is_bit_identical_to_per_output_chains(nh, monkeypatch):
+    """Wide-input rollouts batch all outputs of a step into three launches (MCPILCO_NO_BATCHED_STEP=1 restores the per-output chains
+    on side streams); same device code, so trajectories, cost and gradients must agree bit for bit."""
+    sc = scenarios.ur5_full()
+    gps = nh.native_fit(sc)
+    out = {}
+    for mode in ("batched", "chains"):
+        if mode == "chains":
+            monkeypatch.setenv("MCPILCO_NO_BATCHED_STEP", "1")
+        else:
+            monkeypatch.delenv("MCPILCO_NO_BATCHED_STEP", raising=False)
+        plan, _ = nh.native_plan(sc, gps, need_grad=True)
+        states, inputs = plan.forward(nh.x0_of(sc))
+        gr = plan.backward(grad_cost=1.0)
+        out[mode] = (states.clone(), inputs.clone(), plan.cost_out.clone(), {k: v.clone() for k, v in gr.items() if v is not None})
+    a, b = out["batched"], out["chains"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for k in a[3]:
+        assert torch.equal(a[3][k], b[3][k]), k
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # opt-in INT8 tensor-core contraction with error compensation (SURVEY.md §8 f4).  Stated tolerances: with 8 digit planes the
 # posterior variance agrees with the native fp64 path to 1e-7 relative, with 7 planes to 1e-5 (the north-star bound); the
