@@ -700,13 +700,13 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
 // Stage 2, lane j over its dimension and all four channels: acc[j][c] += Y[n][j] T[n][c] — no cross-lane reduction at all.
 //   sum_n a_n dk_n/dx_j = -2 ils_j^2 (x_j E0 - acc[j][a e]) + w1_j acc[j][a]        (and the same with v for the variance)
 // One warp per particle gives only E * M warps (1200 for UR5: 8 per SM, latency-bound at 67 us per step), so the training points are
-// split over the CTAs of a thread-block cluster (gridDim.z = cluster size = 1, 2 or 4, chosen from N alone): each CTA reduces every
+// split over the CTAs of a thread-block cluster (gridDim.z = cluster size = 1 or 2, chosen from N alone): each CTA reduces every
 // nseg-th tile, the partial sums meet in rank 0 through distributed shared memory in a fixed order (bit-stable), rank 0 finalises.
+// Four warps per CTA and clusters of two keep all CTAs of the UR5 shape resident in one wave (clusters of four with eight-warp CTAs
+// made 1.4 waves: 50 us).
 constexpr int WIDE_TILE = 64;
-static inline int wide_segments(int N) {
-  const int tiles = cdiv(N, WIDE_TILE);
-  return tiles >= 4 ? 4 : (tiles >= 2 ? 2 : 1);
-}
+constexpr int WIDE_WPC = 4;  // warps (= particles) per CTA: 128 threads, 6 resident CTAs per SM
+static inline int wide_segments(int N) { return cdiv(N, WIDE_TILE) >= 2 ? 2 : 1; }
 __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const double* __restrict__ Xs, int M, const double* __restrict__ Xtr,
                                                  const double* __restrict__ alpha, int N, const double* __restrict__ V, int ldv,
                                                  double var_scale, int E, int e, double* __restrict__ mean, double* __restrict__ var,
@@ -716,14 +716,14 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
   const int nseg = (int)cluster.num_blocks(), seg = (int)cluster.block_rank();
   __shared__ double sY[WIDE_TILE][MCP_MAX_D + 1];  // +1: lanes over points read a column without bank conflicts
   __shared__ double sA[WIDE_TILE];
-  __shared__ __align__(32) double sT[8][WIDE_TILE][4];
-  __shared__ double sX[8][MCP_MAX_D], sXw[8][MCP_MAX_D];
+  __shared__ __align__(32) double sT[WIDE_WPC][WIDE_TILE][4];
+  __shared__ double sX[WIDE_WPC][MCP_MAX_D], sXw[WIDE_WPC][MCP_MAX_D];
   __shared__ double sIl[MCP_MAX_D];
-  __shared__ __align__(32) double sG[8][MCP_MAX_D][4];
-  __shared__ double sS[8][4];
+  __shared__ __align__(32) double sG[WIDE_WPC][MCP_MAX_D][4];
+  __shared__ double sS[WIDE_WPC][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int m = min(blockIdx.x * 8 + warp, M - 1);
-  const bool owner = blockIdx.x * 8 + warp < M;
+  const int m = min(blockIdx.x * WIDE_WPC + warp, M - 1);
+  const bool owner = blockIdx.x * WIDE_WPC + warp < M;
   const int D = s.D, np1 = s.n_poly;  // np1 in {0, 1}
   const double off = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0, lam = s.lambda;
   const bool se = s.has_se != 0;
@@ -739,7 +739,7 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
   for (int n0 = seg * WIDE_TILE; n0 < N; n0 += nseg * WIDE_TILE) {
     __syncthreads();  // previous tile fully consumed (first pass: sX / sXw / sIl visible)
     const int cnt = min(WIDE_TILE, N - n0);
-    for (int el = tid; el < WIDE_TILE * D; el += 256) {
+    for (int el = tid; el < WIDE_TILE * D; el += WIDE_WPC * 32) {
       const int i = el / D, j = el - i * D;
       sY[i][j] = (i < cnt) ? Xtr[(size_t)n0 * D + el] : 0.0;
     }
@@ -821,7 +821,7 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
   }
 }
 
-__global__ void __launch_bounds__(256) posterior_reduce_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
+__global__ void __launch_bounds__(WIDE_WPC * 32) posterior_reduce_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
                                                                     int M, const double* __restrict__ Xtr,
                                                                     const double* __restrict__ alpha, int N,
                                                                     const double* __restrict__ V, int ldv, double var_scale, int E,
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(256) posterior_reduce_wide_kernel(const __grid
 }
 
 // the same reduce for ALL outputs in one launch (blockIdx.y = output); a link of a programmatic-dependent-launch chain
-__global__ void __launch_bounds__(256) posterior_reduce_wide_batched_kernel(const McpGpDev* __restrict__ gps, const double* __restrict__ Xs,
+__global__ void __launch_bounds__(WIDE_WPC * 32) posterior_reduce_wide_batched_kernel(const McpGpDev* __restrict__ gps, const double* __restrict__ Xs,
                                                                             int M, const double* __restrict__ V, int ldv, size_t gp_stride,
                                                                             int E, double* __restrict__ mean, double* __restrict__ var,
                                                                             double* __restrict__ jmean, double* __restrict__ jvar) {
@@ -918,7 +918,7 @@ int gp_posterior_batched(const McpGpDev* tab, int E, int D, int nmax, const doub
   MCP_LAUNCH_CHECK();
   if (int err = launch_small_gemm(tab, M, nmax, E, Ks, V, ldk, gp_stride, pdl, st)) return err;
   const int nseg = wide_segments(nmax);  // gp_posterior_batched_ok: every output has this segment count
-  MCP_CUDA(launch_cluster_z(pdl, nseg, posterior_reduce_wide_batched_kernel, dim3(cdiv(M, 8), E, nseg), dim3(256), st, tab, Xs, M, V, ldk,
+  MCP_CUDA(launch_cluster_z(pdl, nseg, posterior_reduce_wide_batched_kernel, dim3(cdiv(M, WIDE_WPC), E, nseg), dim3(WIDE_WPC * 32), st, tab, Xs, M, V, ldk,
                             gp_stride, E, mean, var, jmean, jvar));
   count_launch();
   return MCP_OK;
@@ -973,7 +973,7 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
 #undef MCP_FAST_REDUCE
     } else if (jac && wide_reduce_ok(g.spec)) {
       const int nseg = wide_segments(N);
-      MCP_CUDA(launch_cluster_z(false, nseg, posterior_reduce_wide_kernel, dim3(cdiv(mc, 8), 1, nseg), dim3(256), st, g.spec, xs, mc, g.Xtr,
+      MCP_CUDA(launch_cluster_z(false, nseg, posterior_reduce_wide_kernel, dim3(cdiv(mc, WIDE_WPC), 1, nseg), dim3(WIDE_WPC * 32), st, g.spec, xs, mc, g.Xtr,
                                 g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv));
     } else if (jac) {
       MCP_DISPATCH_D(g.spec.D, (posterior_reduce_kernel<DT, true><<<grid, 256, 0, st>>>(
