@@ -120,7 +120,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -382,12 +382,23 @@ def own_arm(args):
         line["cpu_baseline"] = {"value": Mc * Hc * len(times) / float(np.sum(times)), "unit": "particle-steps/s", "cores": cores, "kind": "port",
                                 "sample": "oracle port (torch CPU fp64 + autograd) of the same workload at M=%d x H=%d per rollout, 2 timed "
                                           "rollouts after 1 warm-up, %d threads" % (Mc, Hc, cores)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout (see __main__)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 — NCCL's version banner, library prints — goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(reference_arm(a) if a.impl == "reference" else own_arm(a))
