@@ -34,3 +34,17 @@ def test_reinforce_policy_control_logic(name):
     np.testing.assert_allclose(res["std_list"], g["std_list"], rtol=1e-12)
     np.testing.assert_allclose(res["w_final"], g["w_final"], rtol=1e-10)     # same optimiser trajectory (lr schedule included)
     assert res["states"].shape == g["states"].shape
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line (library banners and prints go to stderr); the reference arm is the oracle port."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--train-points", "128", "--particles-per-gpu", "32", "--horizon", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "particle-steps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
