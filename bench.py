@@ -321,6 +321,17 @@ def own_arm(args):
     variants = {}
     from mcpilco_b200 import _native as _Nn
     if not args.no_variants and args.ozaki == 0 and _Nn.lib().mcpilco_ozaki_available() and args.train_points >= 4096:
+        REPLAY = 10 ** 6  # rollout counter -> Philox key: the same noise for the fp64 rollout and for each variant
+
+        def replay_step():
+            obj._rollouts = REPLAY
+            c, _ = step()
+            return float(c.detach()), [p.grad.detach().clone() for p in params]
+
+        def grad_rel(ga, gb):
+            return max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-300)) for a, b in zip(ga, gb))
+
+        c_ref, g_ref = replay_step()
         for S, tol in ((8, "posterior variance within 1e-7 relative of the fp64 path (tests/test_gpu_parity.py)"),
                        (7, "posterior variance within 1e-5 relative of the fp64 path")):
             os.environ["MCPILCO_OZAKI"] = str(S)
@@ -336,7 +347,10 @@ def own_arm(args):
             vms = max_over_ranks(e0.elapsed_time(e1)) / 2
             g_ms, g_n, g_fl = ops.prof_read()
             ops.prof_enable(False)
+            c_var, g_var = replay_step()
             variants["ozaki%d" % S] = {"value": M_global * H / (vms * 1e-3), "unit": "particle-steps/s", "ms_per_step": vms, "cost": float(vc.detach()),
+                                       "same_noise_vs_fp64": {"cost_rel_diff": abs(c_var - c_ref) / abs(c_ref), "policy_grad_rel_diff": grad_rel(g_var, g_ref),
+                                                              "note": "one rollout + backward replayed with the fp64 run's Philox key (H = %d steps of error growth)" % H},
                                        "contraction": "int8 tcgen05 tensor cores, %d balanced base-256 digit planes per operand, int32 accumulation in TMEM, "
                                                       "fp64 recombination" % S,
                                        "contraction_tflops_fp64_equivalent": g_fl / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else None,
