@@ -39,6 +39,17 @@ void prof_end(cudaStream_t st, double flops);
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Per-device one-time setup (cudaFuncSetAttribute is per function AND per device): true the first time it is called for the
+// current device with this flag array.
+constexpr int MCP_MAX_DEVICES = 64;
+static inline bool first_time_on_device(bool (&done)[MCP_MAX_DEVICES]) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MCP_MAX_DEVICES) return true;
+  if (done[d]) return false;
+  done[d] = true;
+  return true;
+}
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- device primitives --------------------------------------------------------------------------

@@ -227,11 +227,9 @@ bool dgemm_tma_usable(const double* A, int lda, const double* B, int ldb, const 
 template <bool TRIM>
 static int launch_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc,
                       int tri, int kflags, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MCP_MAX_DEVICES] = {};
+  if (first_time_on_device(configured))
     MCP_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
-    configured = true;
-  }
   CUtensorMap tmA, tmB;
   if (int e = make_map(&tmA, A, M, K, lda)) return e;
   if (int e = make_map(&tmB, B, N, K, ldb)) return e;

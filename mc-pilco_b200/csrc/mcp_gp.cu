@@ -430,11 +430,9 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_gp_precompute(cons
       return MCP_OK;
     }
   };
-  static bool potrf_configured = false;
-  if (!potrf_configured) {
+  static bool potrf_configured[MCP_MAX_DEVICES] = {};
+  if (first_time_on_device(potrf_configured))
     MCP_CUDA(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
-    potrf_configured = true;
-  }
   if (int e = Rec{Kp, I, W, np, st}.node(0, nblk)) return e;
   if (Lfac) {  // export L (lower; the upper part of Kp holds scratch, mask it)
     lower_copy_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Lfac, ld, N);
