@@ -367,11 +367,13 @@ def test_cost_stats_output_and_shard_merge(nh):
     close(std, float(full.cost_out[1]), 1e-10)
 
 
-def test_ur5_true_dimensions_vs_oracle(nh):
+@pytest.mark.parametrize("N", [40, 96, 200])
+def test_ur5_true_dimensions_vs_oracle(nh, N):
     """Config 4 at its real dimensions (D = 24, E = 6, Ds = 12, Du = 6): trajectories, cost and policy gradients against the CPU oracle
-    (own precompute on both sides), plus the single-step posterior and its Jacobians."""
+    (own precompute on both sides), plus the single-step posterior and its Jacobians.  N = 40: one 64-point tile, no cluster split in the
+    wide reduce; 96: two tiles, clusters of two; 200: four tiles with a ragged tail."""
     from mcpilco_b200 import _ops as ops
-    sc = scenarios.ur5_full()
+    sc = scenarios.ur5_full(N=N)
     ref = Hh.oracle_rollout(sc)
     gps = nh.native_fit(sc)
     plan, _ = nh.native_plan(sc, gps, need_grad=True)
