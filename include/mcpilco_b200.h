@@ -172,9 +172,9 @@ typedef struct McpRollout {
 } McpRollout;
 
 typedef struct McpRolloutGrad {
-  const double* grad_states; /* [H, M, Ds] dL/dstates or NULL (fused cost: dL/dcost given by grad_cost) */
+  const double* grad_states; /* [H, M, Ds] dL/dstates or NULL; ADDS to the fused cost's gradient when grad_cost != 0 */
   const double* grad_inputs; /* [H, M, Du] or NULL */
-  double grad_cost;          /* upstream gradient of the fused expected cost */
+  double grad_cost;          /* upstream gradient of the fused expected cost (0 when the loss does not use it) */
   double* g_log_ls;          /* out [Dp]     */
   double* g_centers;         /* out [nb, Dp] */
   double* g_W;               /* out [Du, nb] */

@@ -1,6 +1,7 @@
 // Common device/host helpers for libmcpilco_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -40,15 +41,24 @@ void prof_end(cudaStream_t st, double flops);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-// Per-device one-time setup (cudaFuncSetAttribute is per function AND per device): true the first time it is called for the
-// current device with this flag array.
+// Per-device one-time setup (cudaFuncSetAttribute is per function AND per device).  One process-wide mutex serialises every lazily
+// initialised piece of host state (kernel attributes, side streams, driver entry points): a second thread must not see "done" before the
+// first one has finished the setup.
 constexpr int MCP_MAX_DEVICES = 64;
-static inline bool first_time_on_device(bool (&done)[MCP_MAX_DEVICES]) {
+inline std::mutex& init_mutex() {
+  static std::mutex m;
+  return m;
+}
+template <class Kern>
+static inline cudaError_t ensure_dynamic_smem(bool (&done)[MCP_MAX_DEVICES], Kern kern, int bytes) {
+  std::lock_guard<std::mutex> lock(init_mutex());
   int d = 0;
-  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MCP_MAX_DEVICES) return true;
-  if (done[d]) return false;
-  done[d] = true;
-  return true;
+  cudaError_t e = cudaGetDevice(&d);
+  if (e != cudaSuccess) return e;
+  if (d >= 0 && d < MCP_MAX_DEVICES && done[d]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && d >= 0 && d < MCP_MAX_DEVICES) done[d] = true;
+  return e;
 }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -9,7 +9,7 @@ static int launch(int M, int N, int K, double alpha, const double* A, int lda, c
   auto kern = dgemm_nt_kernel<BM, BN, WM, WN>;
   static bool configured[MCP_MAX_DEVICES] = {};
   constexpr size_t smem = gemm_smem_bytes<BM, BN>();
-  if (first_time_on_device(configured)) MCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MCP_CUDA(ensure_dynamic_smem(configured, kern, (int)smem));
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
   kern<<<grid, 32 * WM * WN, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kflags);
   MCP_LAUNCH_CHECK();

@@ -189,6 +189,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
+  std::lock_guard<std::mutex> lock(init_mutex());
   if (!tried) {
     tried = true;
     void* p = nullptr;
@@ -228,8 +229,7 @@ template <bool TRIM>
 static int launch_tma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc,
                       int tri, int kflags, cudaStream_t st) {
   static bool configured[MCP_MAX_DEVICES] = {};
-  if (first_time_on_device(configured))
-    MCP_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
+  MCP_CUDA(ensure_dynamic_smem(configured, dgemm_tma_kernel<TRIM>, (int)T_SMEM_BYTES));
   CUtensorMap tmA, tmB;
   if (int e = make_map(&tmA, A, M, K, lda)) return e;
   if (int e = make_map(&tmB, B, N, K, ldb)) return e;

@@ -431,8 +431,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_gp_precompute(cons
     }
   };
   static bool potrf_configured[MCP_MAX_DEVICES] = {};
-  if (first_time_on_device(potrf_configured))
-    MCP_CUDA(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+  MCP_CUDA(ensure_dynamic_smem(potrf_configured, potrf_block_kernel, POTRF_SMEM));
   if (int e = Rec{Kp, I, W, np, st}.node(0, nblk)) return e;
   if (Lfac) {  // export L (lower; the upper part of Kp holds scratch, mask it)
     lower_copy_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Lfac, ld, N);

@@ -3,6 +3,9 @@
 // model_learning/Model_learning.py:210-229,670-718 (get_next_state), policy_learning/Policy.py:242-265,
 // 323-335,389-403 (policies), policy_learning/Cost_function.py:25-36,53-182 (costs), and the autograd
 // pass of MC_PILCO.py:522 which mcpilco_rollout_bwd replaces.
+#include <map>
+#include <utility>
+
 #include "mcp_rollout_dev.cuh"
 
 namespace mcp {
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
   for (int k = 0; k < DUT; k++) { wb[k] = (has_b && k < Du) ? pol.W[(size_t)k * nb + b] : 0.0; gw[k] = 0.0; }
   const bool drop = dropout_active(pol, r.noise);
   const double keep_scale = drop ? 1.0 / (1.0 - r.noise.p_dropout) : 1.0;
-  const double cost_w = (r.cost.kind != 0 && g.grad_states == nullptr) ? g.grad_cost / (double)M : 0.0;
+  const double cost_w = (r.cost.kind != 0) ? g.grad_cost / (double)M : 0.0;  // adds to grad_states / grad_inputs when both are given
   const double* polin = (ms.enabled && r.pol_in) ? r.pol_in : r.states;
   __syncthreads();
 
@@ -624,21 +627,24 @@ struct Fan {
   cudaStream_t side[MCP_MAX_E];
   cudaEvent_t fork, join[MCP_MAX_E];
 };
-static Fan* get_fan() {
-  static Fan fans[16];
-  static bool ready[16] = {false};
+static Fan* get_fan(cudaStream_t st) {
+  // one set per (device, launching stream): two host threads driving different streams never share the fork / join events
+  static std::map<std::pair<int, cudaStream_t>, Fan*> fans;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (!ready[dev]) {
-    Fan& f = fans[dev];
-    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    for (int e = 1; e < MCP_MAX_E; e++) {
-      if (cudaStreamCreateWithFlags(&f.side[e], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-      if (cudaEventCreateWithFlags(&f.join[e], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
-    ready[dev] = true;
-  }
-  return &fans[dev];
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(init_mutex());
+  auto key = std::make_pair(dev, st);
+  auto it = fans.find(key);
+  if (it != fans.end()) return it->second;
+  if (fans.size() >= 256) return nullptr;  // callers fall back to running the chains one after the other
+  Fan* f = new Fan();
+  bool ok = cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int e = 1; e < MCP_MAX_E && ok; e++)
+    ok = cudaStreamCreateWithFlags(&f->side[e], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&f->join[e], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) return nullptr;
+  fans[key] = f;
+  return f;
 }
 
 static int bwd_grid(int M) {
@@ -735,7 +741,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   for (int e = 0; e < E; e++) nmax = r->gps[e].N > nmax ? r->gps[e].N : nmax;
   const size_t per_gp = (w.scratch_doubles / (size_t)E) & ~(size_t)31;
   const size_t need_gp = 2 * (size_t)M * (size_t)((nmax + 15) / 16 * 16);
-  Fan* fan = (E > 1 && (size_t)M * nmax <= ((size_t)1 << 22) && per_gp >= need_gp) ? get_fan() : nullptr;
+  Fan* fan = (E > 1 && (size_t)M * nmax <= ((size_t)1 << 22) && per_gp >= need_gp) ? get_fan(st) : nullptr;
   MCP_CUDA(cudaMemcpyAsync(r->states, r->x0, sizeof(double) * (size_t)M * Ds, cudaMemcpyDeviceToDevice, st));
   if (meas) {
     MCP_CUDA(cudaMemcpyAsync(r->pol_in, r->x0, sizeof(double) * (size_t)M * Ds, cudaMemcpyDeviceToDevice, st));
@@ -815,7 +821,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_bwd(const 
   if (int e = check_rollout(r)) return e;
   MCP_CHECK_ARG(g != nullptr, "rollout_bwd: null gradient descriptor");
   MCP_CHECK_ARG(r->H == 1 || r->jac, "rollout_bwd: forward was run without need_grad");
-  MCP_CHECK_ARG(g->grad_states || r->cost.kind != 0, "rollout_bwd: neither grad_states nor a fused cost");
+  MCP_CHECK_ARG(g->grad_states || g->grad_inputs || r->cost.kind != 0, "rollout_bwd: no grad_states, no grad_inputs and no fused cost");
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
   if (int e = carve(r, w)) return e;

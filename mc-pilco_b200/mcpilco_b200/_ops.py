@@ -42,6 +42,22 @@ def _enter(dev):
     return L
 
 
+def _restores_device(fn):
+    """The native entry points make the tensors' device current (kernel launches need it); put the caller's device back afterwards so
+    that an op on cuda:1 does not silently redirect the caller's later `device="cuda"` allocations."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        prev = torch.cuda.current_device() if torch.cuda.is_available() else None
+        try:
+            return fn(*a, **k)
+        finally:
+            if prev is not None and torch.cuda.current_device() != prev:
+                N.lib().mcpilco_set_device(prev)
+    return wrapped
+
+
 def even_ld(n):
     return n + (n & 1)
 
@@ -49,6 +65,7 @@ def even_ld(n):
 # ---------------------------------------------------------------------------------------------------
 # covariance / precompute / posterior
 # ---------------------------------------------------------------------------------------------------
+@_restores_device
 def gp_covariance(spec, X1, X2=None, add_noise=False):
     """k(X1, X2) [+ sigma_n2 I].  GP_prior.py:314-335 and children."""
     X1 = _c(X1, "X1")
@@ -68,6 +85,7 @@ def gp_covariance(spec, X1, X2=None, add_noise=False):
     return K
 
 
+@_restores_device
 def gp_diag_covariance(spec, X):
     """diag k(X, X) without noise.  GP_prior.py:337-347."""
     X = _c(X, "X")
@@ -78,6 +96,7 @@ def gp_diag_covariance(spec, X):
     return out
 
 
+@_restores_device
 def gp_precompute(spec, Xtr, y, want_L=False):
     """alpha [N,1], K^-1 [N,N] (a view of an [N, even_ld(N)] buffer, as the posterior kernels want it) and
     optionally the Cholesky factor L.  GP_prior.py:91-115,130-135."""
@@ -98,6 +117,7 @@ def gp_precompute(spec, Xtr, y, want_L=False):
     return out + (Lbuf[:, :n],) if want_L else out
 
 
+@_restores_device
 def gp_nlml(spec, Xtr, y):
     """Negative marginal log likelihood and its gradient w.r.t. the McpGpSpec fields, as one device tensor (layout:
     include/mcpilco_b200.h, mcpilco_gp_nlml).  GP_prior.py:91-115,179-230; Gaussian_likelihood.py:12-24."""
@@ -113,6 +133,7 @@ def gp_nlml(spec, Xtr, y):
     return out
 
 
+@_restores_device
 def gp_sod_select(spec, X, threshold, order=None):
     """Greedy subset-of-data selection on the device; returns the selected indices (python list, in selection order).
     GP_prior.py:232-257."""
@@ -155,6 +176,7 @@ def kinv_for_kernels(Kinv):
 class FittedGp:
     """One output's fitted GP: what Model_learning keeps per gp_index (Model_learning.py:172-175)."""
 
+    @_restores_device
     def __init__(self, spec, Xtr, alpha, Kinv, var_scale=1.0, ozaki_slices=None):
         """ozaki_slices: None -> environment MCPILCO_OZAKI (default 0 = native FP64 contraction); 7 or 8 -> the opt-in INT8
         tensor-core contraction with error compensation (include/mcpilco_b200.h, mcpilco_ozaki_prepare)."""
@@ -198,8 +220,8 @@ def _gp_array(gps):
 
 
 def _workspace(dev, nbytes, tag):
-    """Grow-only scratch per (device, tag): avoids a cudaMalloc round trip on every step."""
-    key = (dev.index, tag)
+    """Grow-only scratch per (device, stream, tag): avoids a cudaMalloc round trip on every step."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, tag)  # per stream: two streams never share scratch
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
@@ -207,6 +229,7 @@ def _workspace(dev, nbytes, tag):
     return t
 
 
+@_restores_device
 def gp_predict(gps, Xs, jac=False):
     """Posterior mean/var [M, E] (and Jacobians [M, E, D]) of E fitted GPs at Xs.  GP_prior.py:137-155."""
     Xs = _c(Xs, "X_test")
@@ -233,6 +256,7 @@ def gp_predict(gps, Xs, jac=False):
 class RolloutPlan:
     """Everything one rollout needs, flattened: owns the McpRollout struct and keeps every tensor it points to alive."""
 
+    @_restores_device
     def __init__(self, model, gps, policy, pol_tensors, cost=None, cost_traj=None, meas=None, M=1, H=1, p_dropout=0.0,
                  seed=0, particle_offset=0, need_grad=False, eps=None, masks=None, meas_eps=None, device=None, M_global=0):
         self.dev = device or gps[0].Xtr.device
@@ -298,6 +322,7 @@ class RolloutPlan:
             if not t.is_contiguous():
                 raise RuntimeError("rollout: policy tensor %s must be contiguous" % nm)
 
+    @_restores_device
     def forward(self, x0):
         self.x0 = _c(x0, "x0")
         if tuple(self.x0.shape) != (self.M, self.model.Ds):
@@ -307,6 +332,7 @@ class RolloutPlan:
         N.check(self.L.mcpilco_rollout_fwd(C.byref(self.r), _stream(self.dev)))
         return self.states, self.inputs
 
+    @_restores_device
     def backward(self, grad_cost=0.0, grad_states=None, grad_inputs=None, want_gx0=False):
         """Policy-parameter gradients (flat views) of  grad_cost * expected_cost + <grad_states, states> + <grad_inputs, inputs>."""
         if not self.need_grad:
@@ -334,6 +360,7 @@ def launch_count(reset=False):
     return int(N.lib().mcpilco_launch_count(1 if reset else 0))
 
 
+@_restores_device
 def policy_forward(pst, tens, x, t=0, p_dropout=0.0, masks_t=None, seed=0, particle_offset=0):
     """u = pi(x) for a batch of states through the CUDA policy kernel.  Policy.py:242-265,323-335,389-403."""
     x = _c(x, "states")
@@ -360,6 +387,7 @@ def policy_forward(pst, tens, x, t=0, p_dropout=0.0, masks_t=None, seed=0, parti
     return u
 
 
+@_restores_device
 def init_particles(kind, a, b, M, seed=0, particle_offset=0):
     """Initial particles keyed by the global particle id.  kind "gauss": a = mean(s) [n_modes, Ds], b = std(s);
     kind "uniform": a = lower, b = upper bound.  MC_PILCO.py:635-657."""
@@ -381,6 +409,7 @@ def prof_read():
     return ms.value, int(n.value), fl.value
 
 
+@_restores_device
 def ozaki_matmul(A, B, slices=8):
     """A [M, N] @ B[N, N]^T through the INT8 tensor-core contraction (test / benchmark hook)."""
     A, B = _c(A, "A"), _c(B, "B")

@@ -80,7 +80,7 @@ class GP_prior(torch.nn.Module):
 
     def gp_spec(self, D):
         """McpGpSpec of this kernel for a D-dimensional gp input; rebuilt only when a parameter changed."""
-        key = (int(D),) + tuple((id(p), p._version) for p in self.parameters())
+        key = (int(D),) + tuple((id(p), p._version, p.data_ptr(), tuple(p.shape)) for p in self.parameters())  # `p.data = ...` keeps _version
         hit = self._spec_cache.get("k")
         if hit is not None and hit[0] == key:
             return hit[1]

@@ -150,7 +150,9 @@ class Model_learning(torch.nn.Module):
     # ---- what the fused rollout consumes -----------------------------------------------------------------------------
     def fitted_gps(self):
         """[ops.FittedGp] for all outputs; rebuilt when pretrain_gp ran or a list entry was replaced (load_model_from_log)."""
-        key = tuple((id(a), id(k), id(x), float(n), tuple(p._version for p in gp.parameters()))
+        def tkey(t):
+            return None if t is None else (id(t), t._version, t.data_ptr(), tuple(t.shape))
+        key = tuple((tkey(a), tkey(k), tkey(x), float(n), tuple(tkey(p) for p in gp.parameters()))
                     for a, k, x, n, gp in zip(self.alpha_list, self.K_X_inv_list, self.gp_inputs_tr_list, self.norm_list, self.gp_list))
         if self._fitted_cache is None or self._fitted_cache[0] != key:
             gps = []
@@ -160,7 +162,8 @@ class Model_learning(torch.nn.Module):
                 X = self.gp_inputs_tr_list[i]
                 gps.append(ops.FittedGp(self.gp_list[i].gp_spec(X.shape[1]), X, self.alpha_list[i], self.K_X_inv_list[i],
                                         var_scale=float(self.norm_list[i]) ** 2))
-            self._fitted_cache = (key, gps)
+            # the keyed tensors are held (FittedGp keeps Xtr / alpha / Kinv views alive), so an id cannot be recycled under the cache
+            self._fitted_cache = (key, gps, (list(self.alpha_list), list(self.K_X_inv_list), list(self.gp_inputs_tr_list)))
         return self._fitted_cache[1]
 
     def rollout_model_struct(self, Ds, Du, particle_pred=True):

@@ -11,6 +11,7 @@ Two paths, chosen per call:
 import torch
 
 from .. import _pack as P
+from .. import distributed as D
 
 
 def _need_cuda(t):
@@ -33,7 +34,24 @@ class Expected_cost(torch.nn.modules.loss._Loss):
             return fused[2], fused[3]
         _need_cuda(states_sequence)
         costs = self.cost_function(states_sequence, inputs_sequence, trial_index)
-        return torch.sum(torch.mean(costs, 1)), torch.sum(torch.std(costs.detach(), 1))
+        shard = getattr(states_sequence, "_mcp_shard", None)
+        if shard is None:
+            return torch.sum(torch.mean(costs, 1)), torch.sum(torch.std(costs.detach(), 1))
+        # particles sharded over ranks: merge the per-step moments so that every rank sees the GLOBAL cost / std (and takes the same
+        # control-flow decisions in reinforce_policy); the gradient of the global particle mean w.r.t. this shard's costs is 1 / M_global
+        rank, world, group, m_global = shard
+        H, n_local = costs.shape[0], costs.shape[1]
+        rows = costs.reshape(H, n_local, -1).permute(0, 2, 1).reshape(-1, n_local)  # [H * k, M_local]: one row per (step, cost column)
+        local_mean = rows.mean(1)
+        counts = [D.shard(m_global, r, world)[1] for r in range(world)]
+        if counts[rank] != n_local:
+            raise RuntimeError("Expected_cost: states hold %d particles but this rank's shard has %d" % (n_local, counts[rank]))
+        with torch.no_grad():
+            stats = torch.stack([local_mean, ((rows - local_mean.unsqueeze(1)) ** 2).sum(1)], 1)
+            mean, m2 = D.merge_cost_stats(D.gather_cost_stats(stats, group, world), counts)
+            cost_g, std_g = D.expected_cost_from_stats(mean, m2, m_global)
+        local = local_mean.sum() * (n_local / float(m_global))
+        return local + (cost_g - local.detach()), std_g
 
 
 def _on(v, like):

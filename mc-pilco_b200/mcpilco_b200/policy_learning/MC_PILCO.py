@@ -57,10 +57,10 @@ class _ParticleRollout(torch.autograd.Function):
         w_local = plan.M / float(m_global)  # this shard's weight in the global particle mean
         generic = g_states is not None or g_inputs is not None
         if generic:
-            gc = 0.0 if g_cost is None else float(g_cost) * w_local
-            gs = None if g_states is None else (g_states * w_local if world > 1 else g_states)
-            gi = None if g_inputs is None else (g_inputs * w_local if world > 1 else g_inputs)
-            gr = plan.backward(grad_cost=gc, grad_states=gs, grad_inputs=gi, want_gx0=ctx.want_gx0)
+            # g_states / g_inputs are d loss / d (this shard's trajectories) of the GLOBAL loss: Expected_cost weights its local
+            # particle mean by w_local itself when sharded; the fused cost's share (if the loss also uses it) is added in the kernel
+            gc = 0.0 if g_cost is None or plan.cost_out is None else float(g_cost) * w_local
+            gr = plan.backward(grad_cost=gc, grad_states=g_states, grad_inputs=g_inputs, want_gx0=ctx.want_gx0)
             scale = None
         else:
             if g_cost is None:
@@ -150,6 +150,8 @@ class MC_PILCO(torch.nn.Module):
         H, Ds, Du = int(T_control), self.state_dim, self.input_dim
         pol, ml = self.control_policy, self.model_learning
         rank, world, group = D.world()
+        if int(num_particles) < world:
+            raise RuntimeError("apply_policy: %d particles cannot be sharded over %d ranks" % (int(num_particles), world))
         offset, count = D.shard(num_particles, rank, world)
         seed = self._next_seed()
         x0 = self._initial_particles(particles_initial_state_mean, particles_initial_state_var, flg_particles_init_uniform,
@@ -167,6 +169,8 @@ class MC_PILCO(torch.nn.Module):
                                particle_offset=offset, need_grad=need_grad, eps=nz.get("eps"), masks=nz.get("masks"),
                                meas_eps=nz.get("meas_eps"), device=x0.device, M_global=int(num_particles))
         states, inputs, cost, std = _ParticleRollout.apply(plan, x0, (rank, world, group, int(num_particles)), *params)
+        if world > 1:
+            states._mcp_shard = (rank, world, group, int(num_particles))  # Expected_cost's generic path merges across ranks with it
         if fused is not None:
             key = self._trial_index if getattr(self.cost_function, "flg_var_lengthscales", False) else None
             states._mcp_fused_cost = (self.cost_function, key, cost, std)

@@ -56,6 +56,59 @@ def cartpole_sweep(N, nb=200, sigma_n=0.1, se_only=False, seed=0):
             "x0_mean": np.zeros(4), "x0_var": 1e-4 * np.ones(4)}
 
 
+REAL_SHAPES = {  # name -> (config, N, M, H, nb): the reference's own sizes (C1-C4)
+    "c1": ("c1", 300, 400, 60, 200),        # test_mcpilco_cartpole.py:124,199 (SE + MPK(2), SoD-sized training set of a late trial)
+    "c2": ("c2", 300, 400, 60, 200),        # test_mcpilco_cartpole_rbf_ker.py (SE only)
+    "c3": ("c3", 300, 400, 90, 200),        # test_mcpilco4pms_cartpole.py:104,171 (4PMS, T = 1/30 s -> H = 90)
+    "c4": ("c4", 400, 200, 200, 400),       # test_mcpilco_ur5_mujoco.py:127,195 (D = 24, E = 6, Ds = 12, Du = 6)
+    "c1_first_trial": ("c1", 60, 400, 60, 200),
+}
+
+
+def ur5_like(N, H, nb, rs):
+    """UR5 joint-space shape (config 4): Ds = 12, Du = 6, E = 6 outputs, D = 24 gp inputs [dq, sin q, cos q, u], SE + linear kernel,
+    trajectory-tracking policy and cost, on smooth synthetic second-order dynamics."""
+    q = rs.uniform(-1.5, 1.5, (N, 6)); dq = rs.uniform(-2, 2, (N, 6)); u = rs.uniform(-1, 1, (N, 6))
+    X = np.concatenate([dq, np.sin(q), np.cos(q), u], 1)
+    Y = 0.02 * (3 * u - 2 * np.sin(q) - 0.3 * dq) + 0.005 * rs.randn(N, 6)
+    gps = [{"log_ls": np.log(3.0) + 0.1 * rs.randn(24), "lambda": 1.0, "sigma_n": 0.05, "mean": 0.0, "mpk": [0.1 * np.exp(0.1 * rs.randn(25))]}
+           for _ in range(6)]
+    tt = np.linspace(0, 1, H)[:, None]
+    traj = np.concatenate([0.3 * np.sin(2 * tt + np.arange(6)[None] * 0.3), 0.1 * np.cos(2 * tt + np.arange(6)[None] * 0.3)], 1)
+    return dict(name="c4", D=24, Ds=12, Du=6, E=6, N=N, X=X, Y=Y, gps=gps,
+                model={"kind": "speed", "use_trig": True, "angle": list(range(6)), "not_angle": list(range(6, 12)), "vel": list(range(6, 12)),
+                       "pos": list(range(6)), "T": 0.02},
+                policy={"kind": "target", "nb": nb,
+                        "centers": np.concatenate([np.pi / 2 * 2 * (rs.rand(nb, 12) - 0.5), 0.1 * 2 * (rs.rand(nb, 12) - 0.5)], 1),
+                        "lengthscales": np.pi * np.ones(24), "weight": 2 * (rs.rand(6, nb) - 0.5), "u_max": [1.0] * 6, "target_traj": traj,
+                        "bias": None, "scale": None},
+                p_dropout=0.25, cost={"kind": "sat_traj", "target_traj": traj, "ls": np.array([0.5] * 6 + [1.0] * 6)},
+                x0_mean=traj[0].copy(), x0_var=1e-6 * np.ones(12))
+
+
+def real_shape(key, seed=0, N=None, M=None, H=None, nb=None, with_noise=True):
+    """A scenario dict (tests/scenarios.py format) at one of the reference's REAL configuration sizes (REAL_SHAPES), synthetic
+    fitted-like data; `with_noise` adds the injected-noise tensors (eps0, eps, masks, meas_eps) the parity tests feed to both sides."""
+    name, N0, M0, H0, nb0 = REAL_SHAPES[key]
+    N, M, H, nb = N or N0, M or M0, H or H0, nb or nb0
+    rs = np.random.RandomState(7000 + seed)
+    if name in ("c1", "c2", "c3"):
+        sc = cartpole_sweep(N, nb=nb, sigma_n=float(np.exp(-4.2)) if name != "c3" else 0.05, se_only=(name != "c1"), seed=3 + seed)
+        sc["name"] = name
+        if name == "c3":
+            sc["model"]["T"] = 1.0 / 30
+            sc["pms"] = {"std_pos": np.array([3e-3, 3e-3]), "pos_idx": [0, 2], "vel_idx": [1, 3], "fc": 0.5}
+    else:
+        sc = ur5_like(N, H, nb, rs)
+    sc.update(M=M, H=H)
+    if with_noise:
+        sc["eps0"] = rs.randn(M, sc["Ds"]); sc["eps"] = rs.randn(H - 1, M, sc["E"])
+        sc["masks"] = (rs.rand(H, M, nb) >= sc["p_dropout"]).astype(np.float64)
+        if "pms" in sc:
+            sc["meas_eps"] = rs.randn(H - 1, M, 2)
+    return sc
+
+
 def flops_per_particle_step(N_list, D, need_grad=True):
     """ALGORITHMIC flops of one particle-step: sum_i 2 N_i^2 + (20 D + 20) N_i with the backward pass,
     sum_i N_i^2 + (10 D + 10) N_i forward only."""
