@@ -307,15 +307,17 @@ def own_arm(args):
             h.copy_(p.grad.reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the host reads the result
 
-    e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(args.e2e_steps):
+    ms_e2e, e2e_value = None, None
+    if args.e2e_steps > 0:  # 0: skipped (the full north-star shard takes a minute per step; the default run always measures it)
         e2e_step()
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = M_global * H * args.e2e_steps / (ms_e2e * 1e-3)
+        barrier()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e_value = M_global * H * args.e2e_steps / (ms_e2e * 1e-3)
 
     # ---- opt-in variants of the dominant contraction (same workload, same API; reported beside the fp64 headline) ----
     variants = {}
@@ -386,7 +388,7 @@ def own_arm(args):
                          "flops_per_launch": gemm_fl / max(gemm_n, 1), "kernel_share_of_step": gemm_ms / ms,
                          "peak_source": "own measurement on this pool (FP64 is absent from MEASURED_PEAKS.json): profiles/microbench/r01_fp64_peaks.txt"},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.e2e_steps},
+                    "ms_per_step": None if ms_e2e is None else ms_e2e / args.e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "variants": variants}
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()

@@ -8,23 +8,16 @@
 //   * the product keeps the S(S+1)/2 digit-plane products with t + u < S:   A B^T = 2^(eA+eB) sum_w 256^-(w+2) C_w,
 //     C_w = sum_{t+u=w} A_t B_u^T, every C_w an EXACT int32 GEMM (|C_w| <= (w+1) K 2^14 < 2^31 as long as S K <= 65536; a longer
 //     contraction index is cut into segments that are recombined in fp64);
-//   * storing A's planes side by side along K and B's planes in REVERSE order makes every C_w ONE int8 GEMM with
-//     K_eff = (w+1) K over contiguous sub-ranges: S launches instead of S(S+1)/2, no read-modify-write of C;
-//   * a combine kernel sums the S int32 planes from the least significant up, in fp64, and applies the row/column scales.
-// The int8 GEMM runs on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMA-fed, int32 accumulators in TMEM — SASS:
-// UTCIMMA / UTMALDG / LDTM); it is instantiated from the CUTLASS 4.x collective templates vendored in this image (header-only),
-// the slicing, plane layout and combine kernels are hand-written.  S = 8 carries 64 bits per entry (fp64-class results), S = 7
-// carries 56.  Measured accuracy and rates: DESIGN.md §4.
-#include "mcp_common.cuh"
+//   * A's planes are stored side by side along K and B's planes in REVERSE order, so C_w is one contraction with K_eff = (w+1) K over
+//     contiguous sub-ranges of both operands;
+//   * the plane sums are folded from the least significant up, in fp64, and the row / column scales applied last.
+// The digit-plane products run on the 5th-generation tensor cores in ONE hand-written persistent kernel (ozaki_mma_kernel below:
+// TMA -> tcgen05.mma.cta_group::2.kind::i8 -> int32 accumulators in TMEM -> tcgen05.ld -> fp64 recombination in the epilogue), so
+// the int32 planes never exist in memory.  S = 8 carries 64 bits per entry (fp64-class results), S = 7 carries 56.  Measured accuracy
+// and rates: DESIGN.md §4.
+#include <cuda.h>
 
-#ifdef MCP_WITH_CUTLASS
-#include "cute/tensor.hpp"
-#include "cutlass/cutlass.h"
-#include "cutlass/epilogue/collective/collective_builder.hpp"
-#include "cutlass/gemm/collective/collective_builder.hpp"
-#include "cutlass/gemm/device/gemm_universal_adapter.h"
-#include "cutlass/gemm/kernel/gemm_universal.hpp"
-#endif
+#include "mcp_common.cuh"
 
 namespace mcp {
 
@@ -72,75 +65,9 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   }
 }
 
-// ---- combine: V = 2^(eA + eB) sum_w 256^-(w+2) C_w, least significant plane first ---------------------------------
-__global__ void __launch_bounds__(256) ozaki_combine_kernel(const int32_t* __restrict__ C, size_t plane_stride, int ldc, int M, int N, int S,
-                                                            const int32_t* __restrict__ eA, const int32_t* __restrict__ eB,
-                                                            double* __restrict__ V, int ldv, int accumulate) {
-  // four consecutive columns per thread (ldc is a multiple of 4: 16-byte plane loads)
-  const int n = (blockIdx.x * 256 + threadIdx.x) * 4, m = blockIdx.y;
-  if (n >= N || m >= M) return;
-  const int32_t* c = C + (size_t)m * ldc + n;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int w = S - 1; w >= 0; w--) {
-    const int4 q = *reinterpret_cast<const int4*>(c + (size_t)w * plane_stride);
-    const double sc = scalbn(1.0, -8 * (w + 2));
-    acc[0] = fma((double)q.x, sc, acc[0]);
-    acc[1] = fma((double)q.y, sc, acc[1]);
-    acc[2] = fma((double)q.z, sc, acc[2]);
-    acc[3] = fma((double)q.w, sc, acc[3]);
-  }
-  const int ea = eA[m];
-  double* out = V + (size_t)m * ldv + n;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    if (n + i < N) {
-      const double v = scalbn(acc[i], ea + eB[n + i]);
-      out[i] = accumulate ? out[i] + v : v;
-    }
-  }
-}
-
-#ifdef MCP_WITH_CUTLASS
-namespace {
-using namespace cute;
-using ElemAB = int8_t;
-using ElemC = int32_t;
-using TileShape_ = Shape<_256, _256, _128>;  // one MMA tile spans a CTA pair (cta_group::2): each SM holds 128 rows, B is shared
-using ClusterShape_ = Shape<_2, _1, _1>;
-using Epi = typename cutlass::epilogue::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape_, ClusterShape_, cutlass::epilogue::collective::EpilogueTileAuto, ElemC,
-    ElemC, ElemC, cutlass::layout::RowMajor, 4, ElemC, cutlass::layout::RowMajor, 4,
-    cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
-using Main = typename cutlass::gemm::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElemAB, cutlass::layout::RowMajor, 16, ElemAB, cutlass::layout::ColumnMajor, 16, ElemC,
-    TileShape_, ClusterShape_, cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename Epi::SharedStorage))>,
-    cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
-using GemmKernel_ = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, Main, Epi, void>;
-using Gemm_ = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel_>;
-}  // namespace
-
-// C[M,N] (int32, ldc) = A[M,K] (int8, lda) * B[N,K]^T (int8, ldb)
-static int int8_gemm(const int8_t* A, int lda, const int8_t* B, int ldb, int32_t* C, int ldc, int M, int N, int K, void* ws, size_t wsb,
-                     cudaStream_t st) {
-  using SA = typename Gemm_::GemmKernel::StrideA;
-  using SB = typename Gemm_::GemmKernel::StrideB;
-  using SC = typename Gemm_::GemmKernel::StrideC;
-  SA sa = make_stride(int64_t(lda), Int<1>{}, int64_t(0));
-  SB sb = make_stride(int64_t(ldb), Int<1>{}, int64_t(0));
-  SC sc = make_stride(int64_t(ldc), Int<1>{}, int64_t(0));
-  typename Gemm_::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}, {A, sa, B, sb}, {{1, 0}, C, sc, C, sc}};
-  Gemm_ gemm;
-  MCP_CHECK_ARG(gemm.can_implement(args) == cutlass::Status::kSuccess, "ozaki: int8 GEMM %dx%dx%d (lda %d ldb %d ldc %d) not implementable", M, N,
-                K, lda, ldb, ldc);
-  MCP_CHECK_ARG(Gemm_::get_workspace_size(args) <= wsb, "ozaki: int8 GEMM workspace too small");
-  if (gemm.initialize(args, ws, st) != cutlass::Status::kSuccess || gemm.run(st) != cutlass::Status::kSuccess) {
-    set_error("ozaki: int8 GEMM launch failed");
-    return MCP_E_CUDA;
-  }
-  count_launch();
-  return MCP_OK;
-}
-#endif
+// the persistent tcgen05 kernel (mcp_ozaki_mma.cu)
+int ozaki_mma(const int8_t* Ap, const int32_t* Ae, const int8_t* Bp, const int32_t* Be, int M, int N, int S, int nseg, int Ksp, double* V, int ldv,
+              cudaStream_t st);
 
 // segmentation of the contraction index: nseg segments of Ks columns, Ksp = Ks rounded up to the MMA K tile
 struct OzGeom {
@@ -163,9 +90,9 @@ size_t ozaki_plane_bytes(int rows, int K, int S) {
   return (size_t)rows * g.nseg * S * g.Ksp;
 }
 
-// scratch for one contraction of mc particles against N points: A planes + A exponents + S int32 planes + gemm workspace
+// scratch for one contraction of mc particles against N points: A's digit planes + A's exponents
 size_t ozaki_scratch_bytes(int mc, int N, int S) {
-  return align_up(ozaki_plane_bytes(mc, N, S), 256) + align_up((size_t)mc * 4, 256) + (size_t)S * mc * align_up((size_t)N, 4) * 4 + 65536 + 1024;
+  return align_up(ozaki_plane_bytes(mc, N, S), 256) + align_up((size_t)mc * 4, 256) + 1024;
 }
 
 int ozaki_slice(const double* A, int rows, int K, int ld, int S, int reverse, int8_t* planes, int32_t* expo, cudaStream_t st) {
@@ -180,47 +107,20 @@ int ozaki_slice(const double* A, int rows, int K, int ld, int S, int reverse, in
 // V[mc, N] (fp64, ldv) = A[mc, N] (fp64, lda) * Binv^T given B's reversed digit planes / exponents
 int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t* Bplanes, const int32_t* Bexp, double* V, int ldv, void* scratch,
                    size_t scratch_bytes, cudaStream_t st) {
-#ifdef MCP_WITH_CUTLASS
   MCP_CHECK_ARG(scratch_bytes >= ozaki_scratch_bytes(mc, N, S), "ozaki: scratch too small");
   const OzGeom gm = ozaki_geom(N, S);
-  const int ldc = (int)align_up((size_t)N, 4), lda8 = gm.nseg * S * gm.Ksp;
   char* p = (char*)align_up((size_t)scratch, 256);
   int8_t* Ap = (int8_t*)p; p += align_up(ozaki_plane_bytes(mc, N, S), 256);
-  int32_t* Ae = (int32_t*)p; p += align_up((size_t)mc * 4, 256);
-  int32_t* C = (int32_t*)p; p += (size_t)S * mc * ldc * 4;
-  void* gws = (void*)align_up((size_t)p, 256);
-  const size_t plane_stride = (size_t)mc * ldc;
+  int32_t* Ae = (int32_t*)p;
   if (int e = ozaki_slice(A, mc, N, lda, S, 0, Ap, Ae, st)) return e;
-  for (int seg = 0; seg < gm.nseg; seg++) {
-    const int8_t* As = Ap + (size_t)seg * S * gm.Ksp;
-    const int8_t* Bs = Bplanes + (size_t)seg * S * gm.Ksp;
-    for (int w = 0; w < S; w++) {
-      // C_w = [A_0 .. A_w] * [B_w .. B_0]^T : A planes 0..w are the first (w+1) Ksp columns of the segment; the reversed B planes
-      // S-1-w .. S-1 are its last ones
-      if (int e = int8_gemm(As, lda8, Bs + (size_t)(S - 1 - w) * gm.Ksp, lda8, C + w * plane_stride, ldc, mc, N, (w + 1) * gm.Ksp, gws, 65536, st))
-        return e;
-    }
-    ozaki_combine_kernel<<<dim3(cdiv(N, 1024), mc), 256, 0, st>>>(C, plane_stride, ldc, mc, N, S, Ae, Bexp, V, ldv, seg > 0);
-    MCP_LAUNCH_CHECK();
-  }
-  return MCP_OK;
-#else
-  set_error("ozaki: this build has no CUTLASS headers (MCP_WITH_CUTLASS undefined)");
-  return MCP_E_ARG;
-#endif
+  return ozaki_mma(Ap, Ae, Bplanes, Bexp, mc, N, S, gm.nseg, gm.Ksp, V, ldv, st);
 }
 
 }  // namespace mcp
 
 using namespace mcp;
 
-extern "C" __attribute__((visibility("default"))) int mcpilco_ozaki_available(void) {
-#ifdef MCP_WITH_CUTLASS
-  return 1;
-#else
-  return 0;
-#endif
-}
+extern "C" __attribute__((visibility("default"))) int mcpilco_ozaki_available(void) { return 1; }
 
 extern "C" __attribute__((visibility("default"))) size_t mcpilco_ozaki_plane_bytes(int N, int slices) { return ozaki_plane_bytes(N, N, slices); }
 

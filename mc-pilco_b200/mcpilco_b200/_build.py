@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libmcpilco_b200.so")
-SOURCES = ["mcp_abi.cu", "mcp_dgemm.cu", "mcp_dgemm_tma.cu", "mcp_gp.cu", "mcp_nlml.cu", "mcp_sod.cu", "mcp_rollout.cu", "mcp_small.cu", "mcp_ozaki.cu"]
+SOURCES = ["mcp_abi.cu", "mcp_dgemm.cu", "mcp_dgemm_tma.cu", "mcp_gp.cu", "mcp_nlml.cu", "mcp_sod.cu", "mcp_rollout.cu", "mcp_small.cu", "mcp_ozaki.cu", "mcp_ozaki_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -16,17 +16,6 @@ def _newer(src_paths, target):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(p) > t for p in src_paths)
-
-
-def cutlass_flags():
-    """-I flags for the CUTLASS / CuTe headers vendored in this image (only mcp_ozaki.cu uses them); [] if absent, in which case the
-    opt-in INT8 variant reports itself unavailable and everything else is unaffected."""
-    import site
-    for sp in site.getsitepackages():
-        inc = os.path.join(sp, "flashinfer", "data", "cutlass", "include")
-        if os.path.exists(os.path.join(inc, "cute", "arch", "mma_sm100_umma.hpp")):
-            return ["-DMCP_WITH_CUTLASS", "-I" + inc]
-    return []
 
 
 def build(force=False, verbose=False):
@@ -42,8 +31,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(bdir, s.replace(".cu", ".o"))
         objs.append(o)
-        extra = cutlass_flags() if s == "mcp_ozaki.cu" else []
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
