@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 5
+#define MCP_ABI_VERSION 6
 
 #define MCP_MAX_D 32    /* gp-input dimension            */
 #define MCP_MAX_DS 16   /* state dimension               */
@@ -74,7 +74,11 @@ typedef struct McpGp {
   const int8_t* kinv_planes; /* reversed digit planes of Kinv, mcpilco_ozaki_plane_bytes(N, slices) bytes */
   const int32_t* kinv_exp;   /* [N] row exponents */
   int32_t ozaki_slices;      /* 0 (off), 7 (56-bit) or 8 (64-bit operands) */
-  int32_t _pad;
+  int32_t ld_linv;           /* leading dimension of Linv (>= N, even) */
+  /* OPTIONAL triangular factor L^-1 (lower, K + sigma_n2 I = L L^T) from mcpilco_gp_precompute: forward-only predicts / rollouts
+   * (no Jacobians) then form  w = K* L^-T  over the triangle only and  var = k** - |w|^2 : half the flops of K* Kinv.  NULL = not
+   * available (e.g. Kinv came from a log file): the full product is used. */
+  const double* Linv;        /* [N, ld_linv] or NULL */
 } McpGp;
 
 /* ---- state -> gp-input map and integration (Model_learning.py:450-456,471-493,564-579,670-718) ---- */
@@ -200,10 +204,11 @@ int mcpilco_gp_diag_covariance(const McpGpSpec* spec, const double* X, int n, do
 
 /* Per-model-update precompute: K = k(X,X) + sigma_n2 I, blocked Cholesky K = L L^T, R = L^-1,
  * Kinv = R^T R, alpha = Kinv (y - mean0).  Replaces GP_prior.forward / get_alpha (GP_prior.py:91-115,130-135)
- * as driven by Model_learning.pretrain_gp (Model_learning.py:163-208).  Lfac (optional, [N, ld]) receives L. */
+ * as driven by Model_learning.pretrain_gp (Model_learning.py:163-208).  Lfac / Linv (optional, [N, ld], lower triangular with
+ * zeros above the diagonal) receive L and R = L^-1. */
 size_t mcpilco_gp_precompute_workspace_bytes(int N);
 int mcpilco_gp_precompute(const McpGpSpec* spec, const double* Xtr, const double* y, int N, double* alpha,
-                          double* Kinv, int ld, double* Lfac, void* workspace, size_t workspace_bytes, void* stream);
+                          double* Kinv, int ld, double* Lfac, double* Linv, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Greedy subset-of-data selection (GP_prior.get_SOD, gpr_lib/GP_prior/GP_prior.py:232-257): candidates are visited in `order`
  * (DEVICE int array [N], NULL = 0..N-1; order[0] seeds the subset); a candidate joins when the predictive standard deviation of the

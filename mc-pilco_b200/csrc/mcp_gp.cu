@@ -378,7 +378,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_gp_diag_covariance
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_gp_precompute(const McpGpSpec* spec, const double* Xtr, const double* y, int N, double* alpha, double* Kinv,
-                                     int ld, double* Lfac, void* workspace, size_t workspace_bytes, void* stream) {
+                                     int ld, double* Lfac, double* Linv, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_spec(spec)) return e;
   MCP_CHECK_ARG(N >= 1 && Xtr && y && alpha && Kinv && ld >= N, "gp_precompute: bad arguments (N=%d ld=%d)", N, ld);
   MCP_CHECK_ARG(workspace && workspace_bytes >= mcpilco_gp_precompute_workspace_bytes(N), "gp_precompute: workspace too small");
@@ -436,6 +436,11 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_gp_precompute(cons
   if (Lfac) {  // export L (lower; the upper part of Kp holds scratch, mask it)
     lower_copy_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(Kp, np, Lfac, ld, N);
     MCP_LAUNCH_CHECK();
+  }
+  if (Linv) {  // export R = L^-1 (lower): what forward-only posteriors contract with instead of the full Kinv
+    lower_copy_kernel<<<dim3(cdiv(N, 32), cdiv(N, 8)), dim3(32, 8), 0, st>>>(I, np, Linv, ld, N);
+    MCP_LAUNCH_CHECK();
+    if (ld > N) MCP_CUDA(cudaMemset2DAsync(Linv + N, sizeof(double) * ld, 0, sizeof(double) * (ld - N), N, st));
   }
 
   // 4. K^-1 = W W^T (lower tiles, contraction trimmed to k >= max(row blocks)), mirrored into the output
@@ -517,6 +522,43 @@ __global__ void __launch_bounds__(256) posterior_reduce_kernel(const __grid_cons
         }
       }
     }
+  }
+}
+
+
+// Forward-only posterior from the triangular factor: row m of Ks = k(x_m, Xtr) and of W = Ks L^-T given,
+//   mean = mean0 + sum_n alpha_n Ks_n,   var = scale (k** - sum_n W_n^2)      (k*^T Kinv k* = |L^-1 k*|^2).
+// One warp per particle; streams the two rows once (HBM / L2 bound: 16 N bytes per particle).
+template <int DT>
+__global__ void __launch_bounds__(256) posterior_tri_reduce_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs, int M,
+                                                                   const double* __restrict__ alpha, int N, const double* __restrict__ Ks,
+                                                                   const double* __restrict__ W, int ldk, double var_scale, int E, int e,
+                                                                   double* __restrict__ mean, double* __restrict__ var) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const double* k = Ks + (size_t)m * ldk;
+  const double* w = W + (size_t)m * ldk;
+  double mu = 0.0, q = 0.0;
+  int n = lane * 2;
+  for (; n + 1 < N; n += 64) {  // ldk is a multiple of 16 and the scratch base is 256-byte aligned: 16-byte row loads
+    const double2 kk = *reinterpret_cast<const double2*>(k + n), ww = *reinterpret_cast<const double2*>(w + n);
+    const double2 aa = make_double2(alpha[n], alpha[n + 1]);
+    mu = fma(aa.x, kk.x, mu);
+    mu = fma(aa.y, kk.y, mu);
+    q = fma(ww.x, ww.x, q);
+    q = fma(ww.y, ww.y, q);
+  }
+  if (n < N) {
+    mu = fma(alpha[n], k[n], mu);
+    q = fma(w[n], w[n], q);
+  }
+  mu = warp_sum(mu);
+  q = warp_sum(q);
+  if (lane == 0) {
+    double x[DT];
+    KFn<DT>::load(x, Xs + (size_t)m * s.D, s.D);
+    mean[(size_t)m * E + e] = s.mean0 + mu;
+    var[(size_t)m * E + e] = var_scale * (KFn<DT>::kdiag(s, x) - q);
   }
 }
 
@@ -930,6 +972,8 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
                 "gp %d: Kinv must be 16-byte aligned with an even leading dimension >= N (ld=%d N=%d)", e, g.ld_kinv, N);
   const int oz = g.ozaki_slices;
   MCP_CHECK_ARG(oz == 0 || (g.kinv_planes && g.kinv_exp), "gp %d: ozaki_slices set without digit planes", e);
+  MCP_CHECK_ARG(g.Linv == nullptr || (g.ld_linv >= N && g.ld_linv % 2 == 0 && ((uintptr_t)g.Linv % 16) == 0),
+                "gp %d: Linv must be 16-byte aligned with an even leading dimension >= N", e);
   // doubles of scratch per particle: K* and V rows, plus (INT8 variant) digit planes, exponent and the int32 product planes
   size_t per = 2 * (size_t)ldk;
   if (oz) per += (ozaki_scratch_bytes(1024, N, oz) / 1024 + 7) / 8 + 1;
@@ -943,6 +987,20 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     double* V = scratch + (size_t)Mc * ldk;
     const double* xs = Xs + (size_t)m0 * g.spec.D;
     if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
+    if (!jac && !oz && g.Linv != nullptr && dgemm_tma_usable(Ks, ldk, g.Linv, g.ld_linv, V, ldk)) {
+      // forward-only: w = K* L^-T over the triangle (column tile n0 needs k < n0 + tile), var = k** - |w|^2: N^2 instead of 2 N^2 flops
+      prof_begin(st);
+      if ((size_t)cdiv(mc, 128) * cdiv(N, 128) >= 96) {
+        if (int err = dgemm_nt_tma_trim(mc, N, N, 1.0, Ks, ldk, g.Linv, g.ld_linv, 0.0, V, ldk, 0, KF_B_LOWER, st)) return err;
+      } else {
+        if (int err = dgemm_nt(mc, N, N, 1.0, Ks, ldk, g.Linv, g.ld_linv, 0.0, V, ldk, 0, KF_B_LOWER, st)) return err;
+      }
+      prof_end(st, (double)mc * (double)N * (double)N);
+      MCP_DISPATCH_D(g.spec.D, (posterior_tri_reduce_kernel<DT><<<cdiv(mc, 8), 256, 0, st>>>(g.spec, xs, mc, g.alpha, N, Ks, V, ldk, g.var_scale, E, e,
+                                                                                              mean + (size_t)m0 * E, var + (size_t)m0 * E)));
+      MCP_LAUNCH_CHECK();
+      continue;
+    }
     prof_begin(st);
     if (oz) {
       void* osc = (void*)(scratch + 2 * (size_t)Mc * ldk);

@@ -158,7 +158,7 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_gp_nlml(const McpG
   void* pre_ws = p;
   size_t pre_bytes = workspace_bytes - ((char*)pre_ws - (char*)workspace);
   MCP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * mcpilco_gp_nlml_grad_size(), st));
-  if (int e = mcpilco_gp_precompute(spec, X, y, N, alpha, Kinv, (int)ld, Lfac, pre_ws, pre_bytes, stream)) return e;
+  if (int e = mcpilco_gp_precompute(spec, X, y, N, alpha, Kinv, (int)ld, Lfac, nullptr, pre_ws, pre_bytes, stream)) return e;
   nlml_value_kernel<<<1, 256, 0, st>>>(y, alpha, Lfac, (int)ld, N, spec->mean0, out);
   MCP_LAUNCH_CHECK();
   dim3 grid(cdiv(N, 256), cdiv(N, NL_ROWS));

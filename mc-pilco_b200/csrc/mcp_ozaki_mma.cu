@@ -128,6 +128,18 @@ __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, int32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void oz_tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one lane of the (converged) warp; the surrounding code stays warp-uniform so that descriptors and addresses live in uniform registers
+__device__ __forceinline__ bool oz_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void oz_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void oz_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -208,43 +220,46 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   if (warp == 0) {
-    // ------------------------------- TMA producer (both CTAs) -------------------------------
-    if (lane == 0) {
-      uint32_t peA = 0xFFFFu, peB = 0xFFFFu;  // parity to wait for on each slot's `empty` barrier (a fresh barrier passes parity 1)
-      for (int tile = cluster_id; tile < tiles; tile += num_clusters) {
-        const OzTile tl = oz_tile(tile, tiles_m, tiles_n);
-        const int a_row = tl.m0 + (int)rank * OZ_BM, b_row = tl.n0 + (int)rank * (OZ_BN / 2);
-        for (int seg = 0; seg < nseg; seg++) {
-          for (int sw = 0; sw < nsweeps; sw++) {
-            const OzSweep g = oz_sweep(S, sw);
-            for (int kb = 0; kb < kblocks; kb++) {
-              const int kcol = kb * OZ_BK;
-              for (int t = 0; t <= g.whi; t++) {
-                // B planes first needed by A_t (in the order the MMA thread touches them), then A_t itself
-                const int ufirst = t == 0 ? g.wlo : g.wlo - t, ulast = t == 0 ? g.whi : g.wlo - t;
-                for (int u = ufirst; u <= ulast; u++) {
-                  if (u < 0) continue;
-                  const int i = oz_slot(u, kb, g.whi);
-                  oz_mbar_wait(emptyB(i), (peB >> i) & 1u);
-                  peB ^= 1u << i;
+    // ------------------------------- TMA producer (both CTAs; the whole warp runs the loops, one elected lane issues) -------------
+    uint32_t peA = 0xFFFFu, peB = 0xFFFFu;  // parity to wait for on each slot's `empty` barrier (a fresh barrier passes parity 1)
+    for (int tile = cluster_id; tile < tiles; tile += num_clusters) {
+      const OzTile tl = oz_tile(tile, tiles_m, tiles_n);
+      const int a_row = tl.m0 + (int)rank * OZ_BM, b_row = tl.n0 + (int)rank * (OZ_BN / 2);
+      for (int seg = 0; seg < nseg; seg++) {
+        for (int sw = 0; sw < nsweeps; sw++) {
+          const OzSweep g = oz_sweep(S, sw);
+          for (int kb = 0; kb < kblocks; kb++) {
+            const int kcol = kb * OZ_BK;
+            for (int t = 0; t <= g.whi; t++) {
+              // B planes first needed by A_t (in the order the MMA thread touches them), then A_t itself
+              const int ufirst = t == 0 ? g.wlo : g.wlo - t, ulast = t == 0 ? g.whi : g.wlo - t;
+              for (int u = ufirst; u <= ulast; u++) {
+                if (u < 0) continue;
+                const int i = oz_slot(u, kb, g.whi);
+                oz_mbar_wait(emptyB(i), (peB >> i) & 1u);
+                peB ^= 1u << i;
+                if (oz_elect_one()) {
                   if (rank == 0) oz_mbar_expect_tx(fullB(i), 2 * OZ_B_BYTES);  // both CTAs' boxes land on the leader's barrier
                   oz_tma_load_2sm(smemB + (uint32_t)i * OZ_B_BYTES, &tmB, (seg * S + (S - 1 - u)) * Ksp + kcol, b_row, oz_mapa(fullB(i), 0));
                 }
-                const int i = oz_slot(t, kb, g.whi);
-                oz_mbar_wait(emptyA(i), (peA >> i) & 1u);
-                peA ^= 1u << i;
+                __syncwarp();
+              }
+              const int i = oz_slot(t, kb, g.whi);
+              oz_mbar_wait(emptyA(i), (peA >> i) & 1u);
+              peA ^= 1u << i;
+              if (oz_elect_one()) {
                 if (rank == 0) oz_mbar_expect_tx(fullA(i), 2 * OZ_A_BYTES);
                 oz_tma_load_2sm(smemA + (uint32_t)i * OZ_A_BYTES, &tmA, (seg * S + t) * Ksp + kcol, a_row, oz_mapa(fullA(i), 0));
               }
+              __syncwarp();
             }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer (leader CTA, one thread) -------------------------------
-    if (rank == 0 && lane == 0) {
+    // ------------------------------- MMA issuer (leader CTA; the whole warp runs the loops, one elected lane issues) -------------
+    if (rank == 0) {
       uint32_t pfA = 0, pfB = 0, pte = 1;  // parities to wait for: slots' `full` barriers, accumulators drained
       for (int tile = cluster_id; tile < tiles; tile += num_clusters) {
         for (int seg = 0; seg < nseg; seg++) {
@@ -269,20 +284,25 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   oz_fence_after();
                   const uint64_t bdesc = oz_smem_desc(smemB + (uint32_t)ib * OZ_B_BYTES);
                   const uint32_t d_tmem = tmem_base + (uint32_t)(t + u - g.wlo) * OZ_BN;
-#pragma unroll
-                  for (int k = 0; k < OZ_BK / 32; k++)
-                    oz_mma_i8_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, (kb > 0 || t > 0 || k > 0) ? 1u : 0u);
-                  if (t == g.whi - u) oz_commit_pair(emptyB(ib));  // last product of this k-block that reads B_u: slot free in both CTAs
+                  const uint32_t acc0 = (kb > 0 || t > 0) ? 1u : 0u;
+                  if (oz_elect_one()) {
+                    oz_mma_i8_2sm(d_tmem, adesc, bdesc, acc0);
+                    oz_mma_i8_2sm(d_tmem, adesc + 2u, bdesc + 2u, 1u);
+                    oz_mma_i8_2sm(d_tmem, adesc + 4u, bdesc + 4u, 1u);
+                    oz_mma_i8_2sm(d_tmem, adesc + 6u, bdesc + 6u, 1u);
+                    if (t == g.whi - u) oz_commit_pair(emptyB(ib));  // last product of this k-block that reads B_u: slot free in both CTAs
+                    if (u == uhi) oz_commit_pair(emptyA(ia));        // ... and A_t
+                  }
+                  __syncwarp();
                 }
-                oz_commit_pair(emptyA(ia));
               }
             }
-            oz_commit_pair(tfull);  // the sweep's plane sums are complete in both CTAs' tensor memory
+            if (oz_elect_one()) oz_commit_pair(tfull);  // the sweep's plane sums are complete in both CTAs' tensor memory
+            __syncwarp();
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs): TMEM -> fp64 recombination into V -------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may read

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 MAX_D, MAX_DS, MAX_DU, MAX_E, MAX_DP, MAX_POLY, MAX_DEG = 32, 16, 8, 16, 32, 3, 3
-ABI_VERSION = 5
+ABI_VERSION = 6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcpilco_b200.so")
 
@@ -22,7 +22,7 @@ class GpSpec(C.Structure):
 class Gp(C.Structure):
     _fields_ = [("spec", GpSpec), ("N", C.c_int32), ("ld_kinv", C.c_int32), ("Xtr", C.c_void_p), ("alpha", C.c_void_p),
                 ("Kinv", C.c_void_p), ("var_scale", C.c_double), ("kinv_planes", C.c_void_p), ("kinv_exp", C.c_void_p),
-                ("ozaki_slices", C.c_int32), ("_pad", C.c_int32)]
+                ("ozaki_slices", C.c_int32), ("ld_linv", C.c_int32), ("Linv", C.c_void_p)]
 
 
 class Model(C.Structure):
@@ -79,7 +79,7 @@ SYMBOLS = {
     "mcpilco_gp_diag_covariance": (C.c_int, [C.POINTER(GpSpec), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mcpilco_gp_precompute_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mcpilco_gp_precompute": (C.c_int, [C.POINTER(GpSpec), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mcpilco_gp_sod_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mcpilco_gp_sod_select": (C.c_int, [C.POINTER(GpSpec), C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.c_void_p]),

@@ -97,9 +97,10 @@ def gp_diag_covariance(spec, X):
 
 
 @_restores_device
-def gp_precompute(spec, Xtr, y, want_L=False):
-    """alpha [N,1], K^-1 [N,N] (a view of an [N, even_ld(N)] buffer, as the posterior kernels want it) and
-    optionally the Cholesky factor L.  GP_prior.py:91-115,130-135."""
+def gp_precompute(spec, Xtr, y, want_L=False, want_Linv=False):
+    """alpha [N,1], K^-1 [N,N] (a view of an [N, even_ld(N)] buffer, as the posterior kernels want it) and optionally the
+    Cholesky factor L and / or its inverse R = L^-1 (lower triangular; what forward-only posteriors contract with).
+    GP_prior.py:91-115,130-135."""
     Xtr, y = _c(Xtr, "X"), _c(y, "Y").reshape(-1)
     L_ = _enter(Xtr.device)
     n = Xtr.shape[0]
@@ -109,12 +110,17 @@ def gp_precompute(spec, Xtr, y, want_L=False):
     alpha = torch.empty(n, dtype=F64, device=Xtr.device)
     Kbuf = torch.zeros(n, ld, dtype=F64, device=Xtr.device)
     Lbuf = torch.zeros(n, ld, dtype=F64, device=Xtr.device) if want_L else None
+    Rbuf = torch.zeros(n, ld, dtype=F64, device=Xtr.device) if want_Linv else None
     wsb = L_.mcpilco_gp_precompute_workspace_bytes(n)
     ws = torch.empty(wsb, dtype=torch.uint8, device=Xtr.device)
-    N.check(L_.mcpilco_gp_precompute(C.byref(spec), _ptr(Xtr), _ptr(y), n, _ptr(alpha), _ptr(Kbuf), ld, _ptr(Lbuf), _ptr(ws), wsb,
+    N.check(L_.mcpilco_gp_precompute(C.byref(spec), _ptr(Xtr), _ptr(y), n, _ptr(alpha), _ptr(Kbuf), ld, _ptr(Lbuf), _ptr(Rbuf), _ptr(ws), wsb,
                                      _stream(Xtr.device)))
     out = (alpha.reshape(n, 1), Kbuf[:, :n])
-    return out + (Lbuf[:, :n],) if want_L else out
+    if want_L:
+        out = out + (Lbuf[:, :n],)
+    if want_Linv:
+        out = out + (Rbuf[:, :n],)
+    return out
 
 
 @_restores_device
@@ -173,17 +179,35 @@ def kinv_for_kernels(Kinv):
     return buf[:, :n], buf.stride(0)
 
 
+def attach_linv(Kinv, Linv):
+    """Remember the triangular factor L^-1 that belongs to this K^-1 tensor (valid while the tensor is not modified in place)."""
+    Kinv._mcp_linv = (Linv, Kinv._version, Kinv.data_ptr())
+
+
+def attached_linv(Kinv):
+    tag = getattr(Kinv, "_mcp_linv", None)
+    if tag is None or tag[1] != Kinv._version or tag[2] != Kinv.data_ptr():
+        return None
+    return tag[0]
+
+
 class FittedGp:
     """One output's fitted GP: what Model_learning keeps per gp_index (Model_learning.py:172-175)."""
 
     @_restores_device
-    def __init__(self, spec, Xtr, alpha, Kinv, var_scale=1.0, ozaki_slices=None):
+    def __init__(self, spec, Xtr, alpha, Kinv, var_scale=1.0, ozaki_slices=None, Linv=None):
         """ozaki_slices: None -> environment MCPILCO_OZAKI (default 0 = native FP64 contraction); 7 or 8 -> the opt-in INT8
         tensor-core contraction with error compensation (include/mcpilco_b200.h, mcpilco_ozaki_prepare)."""
         self.spec = spec
         self.Xtr = _c(Xtr, "gp_inputs")
         self.alpha = _c(alpha, "alpha").reshape(-1)
         self.Kinv, self.ld = kinv_for_kernels(Kinv)
+        # optional triangular factor L^-1 (gp_precompute(want_Linv=True)): forward-only posteriors / rollouts then cost N^2 flops
+        if Linv is None:
+            Linv = attached_linv(Kinv)
+        self.Linv, self.ld_linv = kinv_for_kernels(Linv) if Linv is not None else (None, 0)
+        if self.Linv is not None and self.Linv.shape[0] != self.Kinv.shape[0]:
+            raise RuntimeError("FittedGp: Linv and Kinv sizes differ")
         self.var_scale = float(var_scale)
         self.N = self.Xtr.shape[0]
         if self.Xtr.shape[1] != spec.D or self.alpha.numel() != self.N or self.Kinv.shape[0] != self.N:
@@ -210,6 +234,7 @@ class FittedGp:
         g.ozaki_slices = self.ozaki
         g.kinv_planes = self.planes.data_ptr() if self.planes is not None else None
         g.kinv_exp = self.plane_exp.data_ptr() if self.plane_exp is not None else None
+        g.Linv, g.ld_linv = (self.Linv.data_ptr(), self.ld_linv) if self.Linv is not None else (None, 0)
 
 
 def _gp_array(gps):

@@ -146,7 +146,10 @@ class GP_prior(torch.nn.Module):
 
     def get_alpha(self, X, Y):
         """alpha = K_X^-1 (Y - m_X)  (reference :130-135)."""
-        alpha, K_X_inv = ops.gp_precompute(self.gp_spec(X.shape[1]), X, Y)
+        alpha, K_X_inv, Linv = ops.gp_precompute(self.gp_spec(X.shape[1]), X, Y, want_Linv=True)
+        # the triangular factor rides along on the K_X_inv tensor object (the reference's return signature has no slot for it):
+        # forward-only posteriors built from THIS tensor use it; any other K_X_inv (a loaded log, a modified copy) takes the full product
+        ops.attach_linv(K_X_inv, Linv)
         return alpha, self.get_mean(X), K_X_inv
 
     def get_estimate_from_alpha(self, X, X_test, alpha, m_X, K_X_inv=None, Y_test=None):

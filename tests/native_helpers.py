@@ -22,11 +22,12 @@ def native_fit(sc, golden=None):
     X = G(sc["X"])
     gps = []
     for e, sp in enumerate(native_specs(sc)):
-        if golden is None:
-            alpha, Kinv = ops.gp_precompute(sp, X, G(sc["Y"][:, e:e + 1]))
+        Linv = None
+        if golden is None:  # own precompute: the triangular factor comes along, so forward-only rollouts take the N^2 path
+            alpha, Kinv, Linv = ops.gp_precompute(sp, X, G(sc["Y"][:, e:e + 1]), want_Linv=True)
         else:
             alpha, Kinv = G(golden[f"alpha_{e}"]), G(golden[f"Kinv_{e}"])
-        gps.append(ops.FittedGp(sp, X, alpha, Kinv))
+        gps.append(ops.FittedGp(sp, X, alpha, Kinv, Linv=Linv))
     return gps
 
 

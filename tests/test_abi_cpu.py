@@ -141,7 +141,7 @@ def test_argument_errors_are_reported_before_any_cuda_work(native):
     assert L.mcpilco_gp_covariance(C.byref(bad), None, 4, None, 4, 0, None, 4, None) == E_ARG and b"gp input dim 99" in L.mcpilco_last_error()
     empty = P.new_gp_spec(3)
     assert L.mcpilco_gp_diag_covariance(C.byref(empty), None, 4, None, None) == E_ARG and b"empty kernel" in L.mcpilco_last_error()
-    assert L.mcpilco_gp_precompute(C.byref(spec), None, None, 0, None, None, 0, None, None, 0, None) == E_ARG
+    assert L.mcpilco_gp_precompute(C.byref(spec), None, None, 0, None, None, 0, None, None, None, 0, None) == E_ARG
     assert L.mcpilco_gp_predict(None, 0, None, 5, None, None, None, None, None, 0, None) == E_ARG and b"bad E" in L.mcpilco_last_error()
     assert L.mcpilco_gp_nlml(C.byref(spec), None, None, 5, None, None, 0, None) == E_ARG
     assert L.mcpilco_gp_sod_select(C.byref(spec), None, 5, None, 0.1, None, None, None, 0, None) == E_ARG

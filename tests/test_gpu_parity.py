@@ -341,6 +341,41 @@ def test_posterior_tiles_and_tails(nh, N, M):
     assert torch.isfinite(jm).all() and torch.isfinite(jv).all()
 
 
+@pytest.mark.parametrize("N,M", [(1, 3), (61, 40), (300, 77), (1000, 513), (2003, 800), (4096, 300)])
+def test_forward_only_triangular_form_matches_full_product(nh, N, M):
+    """No Jacobians wanted (no-grad rollouts, reference MC_PILCO.py:430-456; get_estimate_from_alpha): with the triangular factor
+    R = L^-1 from the precompute the posterior is  var = k** - |R k*|^2  through a contraction trimmed to the triangle (half the
+    flops); it must agree with the reference's full form  k** - k*^T Kinv k*  (and R must be the inverse factor of Kinv)."""
+    from mcpilco_b200 import _ops as ops
+    from mcpilco_b200 import _pack as P
+    rs = np.random.RandomState(N + M)
+    spec = P.spec_from_dict({"D": 6, "log_ls": [2, 2, 2, 0.8, 1.5, 2.5], "lambda": 1.0, "mean": 0.02,
+                             "mpk": [np.exp([-5, -5, -5, -4, -4, -4, -3.0]), np.exp([-5, -5, -4, -2, -1, -4.0] * 2)], "sigma_n": 0.1})
+    X = nh.G(rs.uniform(-2, 2, (N, 6)))
+    y = nh.G(rs.randn(N, 1))
+    Xs = nh.G(rs.uniform(-2, 2, (M, 6)))
+    alpha, Kinv, R = ops.gp_precompute(spec, X, y, want_Linv=True)
+    assert torch.equal(R, torch.tril(R))
+    close(R.t() @ R, Kinv.cpu().numpy(), 1e-9, 1e-9 * float(Kinv.abs().max()))
+    m_full, v_full = ops.gp_predict([ops.FittedGp(spec, X, alpha, Kinv)], Xs)
+    m_tri, v_tri = ops.gp_predict([ops.FittedGp(spec, X, alpha, Kinv, Linv=R)], Xs)
+    close(m_tri, m_full.cpu().numpy(), 1e-10, 1e-10)
+    kd = ops.gp_diag_covariance(spec, Xs)
+    close(kd - v_tri[:, 0], (kd - v_full[:, 0]).cpu().numpy(), 1e-9)   # the quadratic forms agree to rounding
+    close(v_tri, v_full.cpu().numpy(), 1e-6, 1e-12)
+    assert (v_tri > 0).all()
+    # with Jacobians the full product is taken either way: bit-identical
+    a = ops.gp_predict([ops.FittedGp(spec, X, alpha, Kinv, Linv=R)], Xs, jac=True)
+    b = ops.gp_predict([ops.FittedGp(spec, X, alpha, Kinv)], Xs, jac=True)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+    # the class API hands the factor along on the K_X_inv tensor it returns
+    assert ops.attached_linv(Kinv) is None
+    ops.attach_linv(Kinv, R)
+    assert ops.attached_linv(Kinv) is R and ops.FittedGp(spec, X, alpha, Kinv).Linv is not None
+    Kinv.mul_(1.0)                                                    # modified in place: the attachment is no longer trusted
+    assert ops.attached_linv(Kinv) is None
+
+
 def test_cost_stats_output_and_shard_merge(nh):
     """The per-step {mean, M2} statistics the rollout exports are what two half-size shards need to rebuild the global
     Expected_cost (single GPU here: the two shards run one after the other; the collectives are covered by the gloo test)."""
