@@ -175,6 +175,47 @@ __device__ __forceinline__ OzSweep oz_sweep(int S, int i) {
 // slot of plane p in k-block kb: sweeps with at most 4 planes keep two k-blocks in flight
 __device__ __forceinline__ int oz_slot(int p, int kb, int whi) { return whi < OZ_SLOTS / 2 ? p + (OZ_SLOTS / 2) * (kb & 1) : p; }
 
+// One sweep of the MMA issuer over the contraction index with the plane-sum range [WLO, WHI] known at compile time: the product schedule
+// of a k-block (which planes meet, which accumulator they feed, where a slot is first needed and where it is released) unrolls into
+// straight-line code — per product one (rare) barrier wait, four UTCIMMA from uniform registers and the commits.  The whole warp runs
+// it; one elected lane issues.  bars: fullA at +0, fullB at +8 SLOTS, emptyA at +16 SLOTS, emptyB at +24 SLOTS (bytes: x8).
+template <int WLO, int WHI>
+__device__ __forceinline__ void oz_mma_sweep(uint32_t smemA, uint32_t smemB, uint32_t bars, uint32_t tmem_base, int kblocks, uint32_t& pfA,
+                                             uint32_t& pfB) {
+  constexpr bool DBL = WHI < OZ_SLOTS / 2;  // at most four planes: two k-blocks in flight (slot = plane + 4 (kb & 1))
+  constexpr uint32_t USED = (1u << (WHI + 1)) - 1u;
+  const uint64_t descA0 = oz_smem_desc(smemA), descB0 = oz_smem_desc(smemB);
+  for (int kb = 0; kb < kblocks; kb++) {
+    const int so = DBL ? (kb & 1) * (OZ_SLOTS / 2) : 0;
+#pragma unroll
+    for (int t = 0; t <= WHI; t++) {
+      const int ia = t + so;
+      oz_mbar_wait(bars + 8u * (uint32_t)ia, (pfA >> ia) & 1u);
+      const uint64_t adesc = descA0 + (uint64_t)(ia * (OZ_A_BYTES >> 4));
+#pragma unroll
+      for (int u = 0; u <= WHI; u++) {
+        if (u < (WLO - t > 0 ? WLO - t : 0) || u > WHI - t) continue;  // the products of this sweep: WLO <= t + u <= WHI
+        const int ib = u + so;
+        if (t == (WLO - u > 0 ? WLO - u : 0)) oz_mbar_wait(bars + 8u * (uint32_t)(OZ_SLOTS + ib), (pfB >> ib) & 1u);  // first use of B_u
+        oz_fence_after();
+        const uint64_t bdesc = descB0 + (uint64_t)(ib * (OZ_B_BYTES >> 4));
+        const uint32_t d_tmem = tmem_base + (uint32_t)((t + u - WLO) * OZ_BN);
+        if (oz_elect_one()) {
+          oz_mma_i8_2sm(d_tmem, adesc, bdesc, (t > 0 || kb > 0) ? 1u : 0u);
+          oz_mma_i8_2sm(d_tmem, adesc + 2u, bdesc + 2u, 1u);
+          oz_mma_i8_2sm(d_tmem, adesc + 4u, bdesc + 4u, 1u);
+          oz_mma_i8_2sm(d_tmem, adesc + 6u, bdesc + 6u, 1u);
+          if (t == WHI - u) oz_commit_pair(bars + 8u * (uint32_t)(3 * OZ_SLOTS + ib));  // last use of B_u in this k-block
+          if (u == WHI - t) oz_commit_pair(bars + 8u * (uint32_t)(2 * OZ_SLOTS + ia));  // ... and of A_t
+        }
+        __syncwarp();
+      }
+    }
+    pfA ^= USED << so;
+    pfB ^= USED << so;
+  }
+}
+
 }  // namespace
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
@@ -268,7 +309,12 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             oz_mbar_wait(tempty, pte);  // the epilogue has read the previous sweep's sums out of tensor memory
             pte ^= 1u;
             oz_fence_after();
-            for (int kb = 0; kb < kblocks; kb++) {
+            if (g.wlo == 4 && g.whi == 7) oz_mma_sweep<4, 7>(smemA, smemB, bars, tmem_base, kblocks, pfA, pfB);        // S = 8, low sums
+            else if (g.wlo == 0 && g.whi == 3) oz_mma_sweep<0, 3>(smemA, smemB, bars, tmem_base, kblocks, pfA, pfB);   // S = 8, high sums
+            else if (g.wlo == 3 && g.whi == 6) oz_mma_sweep<3, 6>(smemA, smemB, bars, tmem_base, kblocks, pfA, pfB);   // S = 7, low sums
+            else if (g.wlo == 0 && g.whi == 2) oz_mma_sweep<0, 2>(smemA, smemB, bars, tmem_base, kblocks, pfA, pfB);   // S = 7, high sums
+            else
+            for (int kb = 0; kb < kblocks; kb++) {  // any other plane count: the same schedule with run-time bounds
               for (int t = 0; t <= g.whi; t++) {
                 const int ia = oz_slot(t, kb, g.whi);
                 oz_mbar_wait(fullA(ia), (pfA >> ia) & 1u);
