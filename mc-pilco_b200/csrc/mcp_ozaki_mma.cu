@@ -23,8 +23,8 @@
 //   * persistent: cluster c processes tiles c, c + #clusters, ... in a grouped raster order (8 tile rows per group) so that the
 //     clusters running at the same time read a compact set of operand panels through L2.
 //
-// Warp roles per CTA (256 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + (leader CTA) MMA issuer (one lane),
-// warps 4..7 = epilogue (TMEM lane quarter = warp % 4); warps 2, 3 idle.
+// Warp roles per CTA (384 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + (leader CTA) MMA issuer (one lane),
+// warps 4..11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4); warps 2, 3 idle.
 #include <cuda.h>
 
 #include "mcp_common.cuh"
@@ -39,7 +39,8 @@ constexpr int OZ_BK = 128;                       // contraction bytes per k-bloc
 constexpr int OZ_SLOTS = 8;                      // plane slots per operand
 constexpr int OZ_A_BYTES = OZ_BM * OZ_BK;        // 16 KB
 constexpr int OZ_B_BYTES = (OZ_BN / 2) * OZ_BK;  // 8 KB
-constexpr int OZ_THREADS = 256;
+constexpr int OZ_EPI_WARPS = 8;                  // two per TMEM lane quarter, 64 output columns each
+constexpr int OZ_THREADS = 32 * (4 + OZ_EPI_WARPS);
 constexpr int OZ_GROUP = 8;                      // tile rows per raster group
 constexpr int OZ_NACC = 4;                       // plane sums resident in tensor memory
 constexpr int OZ_NBAR = 4 * OZ_SLOTS + 2;
@@ -245,7 +246,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       oz_mbar_init(emptyB(i), 1);
     }
     oz_mbar_init(tfull, 1);
-    oz_mbar_init(tempty, 8);  // 4 epilogue warps x 2 CTAs
+    oz_mbar_init(tempty, 2 * OZ_EPI_WARPS);  // every epilogue warp of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -351,7 +352,9 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs): TMEM -> fp64 recombination into V -------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may read
+    constexpr int CHUNKS = OZ_BN / 16 / (OZ_EPI_WARPS / 4);    // 16-column chunks per warp
+    const int c_first = ((warp - 4) >> 2) * CHUNKS;
     uint32_t ptf = 0;
     const uint32_t tempty0 = oz_mapa(tempty, 0);
     for (int tile = cluster_id; tile < tiles; tile += num_clusters) {
@@ -370,13 +373,13 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           oz_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-          for (int c = 0; c < OZ_BN / 16; c++) {
+          for (int c = c_first; c < c_first + CHUNKS; c++) {
             int32_t r[OZ_NACC][16];
 #pragma unroll
             for (int a = 0; a < OZ_NACC; a++)
               if (a < nacc) oz_tmem_ld16(taddr + (uint32_t)(a * OZ_BN + c * 16), r[a]);
             oz_tmem_wait();
-            if (c == OZ_BN / 16 - 1) {  // everything of this sweep is in registers: hand the tensor memory back to the MMA thread
+            if (c == c_first + CHUNKS - 1) {  // everything this warp reads of the sweep is in registers: hand the tensor memory back to the MMA thread
               oz_fence_before();
               __syncwarp();
               if (lane == 0) oz_mbar_arrive_cluster(tempty0);
