@@ -567,28 +567,45 @@ __global__ void __launch_bounds__(256) posterior_tri_reduce_kernel(const __grid_
 // factored so that the particle-dependent coefficients leave the n-loop,
 //   sum_n a_n dk_n/dx_j = -2 ils_j^2 (x_j E0 - E1_j) + sum_{p,f} w_pfj C_pfj,
 //   E0 = sum_n a_n e_n,  E1_j = sum_n a_n e_n y_nj,  C_pfj = sum_n a_n c_pf,n y_nj,  c_pf,n = prod_{g != f} L_pg,n,
-// for the two weight channels a = alpha (mean) and a = V (variance).  Per (particle, training point) this is ~4D+5 FMAs per
-// channel plus one kernel evaluation (5D + exp), about 2.2x fewer FP64 instructions than differentiating k point by point.
+// for the two weight channels a = alpha (mean) and a = V (variance).  The kernel VALUE k_n is not evaluated again: the K* row the
+// contraction consumed is streamed in beside the V row, the (cheap) polynomial factors are rebuilt from the particle-scaled weights
+// and the squared-exponential part is e_n = k_n - poly_n — no distance, no exp.  Per (particle, training point) that leaves ~4D + 5
+// FMAs per channel plus ~3D for the polynomial factors.
 // NP = number of polynomial terms; term p has degree p + 1 (get_Volterra_MPK_GP, Sparse_GP.py:671-737).
-constexpr int RED_TILE = 256;    // training points staged per tile
-constexpr int RED_THREADS = 128;  // 4 particles per block: with ~240 registers per thread two blocks share an SM, so one block's
-                                  // barriers and cp.async waits overlap with the other's FP64 work
+constexpr int RED_TILE = 256;     // training points staged per tile
+constexpr int RED_THREADS = 128;  // 4 particles per block; two blocks share an SM, so one block's barriers and cp.async waits overlap
+                                  // with the other's FP64 work
+constexpr int RED_PB = RED_THREADS / 32;
+// row stride of the transposed training-input tile: staging writes (thread <-> (point, dimension), dimension fastest) then spread over
+// the shared-memory banks instead of piling D-fold on one (16.9 M bank conflicts per launch with a stride of 256)
+template <int DT>
+constexpr int red_yld() { return RED_TILE + (DT <= 4 ? 4 : DT <= 6 ? 3 : 2); }
+template <int DT>
+constexpr size_t red_smem_bytes() {
+  return sizeof(double) * (size_t)(2 * 2 * RED_PB * RED_TILE + 2 * RED_TILE + 2 * DT * red_yld<DT>());
+}
 template <int DT, int NP>
 __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
                                                                     int M, const double* __restrict__ Xtr,
                                                                     const double* __restrict__ alpha, int N,
-                                                                    const double* __restrict__ V, int ldv, double var_scale, int E,
-                                                                    int e, double* __restrict__ mean, double* __restrict__ var,
-                                                                    double* __restrict__ jmean, double* __restrict__ jvar) {
-  // training inputs (transposed: sY[buf][j][i], conflict-free for lane <-> point) and alpha, double-buffered by cp.async;
-  // the warps of the block (one particle each) share them
-  __shared__ double sY[2][DT][RED_TILE];
-  __shared__ double sA[2][RED_TILE];
+                                                                    const double* __restrict__ Ks, const double* __restrict__ V, int ldv,
+                                                                    double var_scale, int E, int e, double* __restrict__ mean,
+                                                                    double* __restrict__ var, double* __restrict__ jmean,
+                                                                    double* __restrict__ jvar) {
+  // double-buffered by cp.async: per warp (= particle) its K* and V rows; shared by the block: alpha and the training inputs
+  // (transposed, sY[buf][j][i]: conflict-free for lane <-> point)
+  extern __shared__ __align__(16) double red_smem[];
+  constexpr int YLD = red_yld<DT>();
+  double(*sK)[RED_PB][RED_TILE] = reinterpret_cast<double(*)[RED_PB][RED_TILE]>(red_smem);
+  double(*sV)[RED_PB][RED_TILE] = reinterpret_cast<double(*)[RED_PB][RED_TILE]>(red_smem + 2 * RED_PB * RED_TILE);
+  double(*sA)[RED_TILE] = reinterpret_cast<double(*)[RED_TILE]>(red_smem + 4 * RED_PB * RED_TILE);
+  double(*sY)[DT][YLD] = reinterpret_cast<double(*)[DT][YLD]>(red_smem + 4 * RED_PB * RED_TILE + 2 * RED_TILE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  constexpr int PB = RED_THREADS / 32;  // particles per block
-  const int m = min(blockIdx.x * PB + warp, M - 1);  // surplus warps shadow the last particle (they still help staging)
-  const bool owner = blockIdx.x * PB + warp < M;
+  const int m = min(blockIdx.x * RED_PB + warp, M - 1);  // surplus warps shadow the last particle (they still help staging)
+  const bool owner = blockIdx.x * RED_PB + warp < M;
   const int D = s.D;
+  const double* krow = Ks + (size_t)m * ldv;
+  const double* vrow = V + (size_t)m * ldv;
   auto stage = [&](int t, int buf) {
     const int n0 = t * RED_TILE;
     for (int el = tid; el < RED_TILE * D; el += RED_THREADS) {
@@ -596,12 +613,18 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
       cp_async8(&sY[buf][j][i], Xtr + (size_t)min(n0 + i, N - 1) * D + j, (n0 + i < N) ? 8 : 0);
     }
     for (int i = tid; i < RED_TILE; i += RED_THREADS) cp_async8(&sA[buf][i], alpha + min(n0 + i, N - 1), (n0 + i < N) ? 8 : 0);
+#pragma unroll
+    for (int c = 0; c < RED_TILE / 64; c++) {  // rows are 16-byte aligned (ld a multiple of 16 doubles); entries past N arrive as zeros
+      const int i = 2 * (lane + 32 * c), left = N - (n0 + i);
+      const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+      const int src = left > 0 ? n0 + i : 0;
+      cp_async16(&sK[buf][warp][i], krow + src, bytes);
+      cp_async16(&sV[buf][warp][i], vrow + src, bytes);
+    }
     cp_async_commit();
   };
-  double x[DT], xs[DT];
+  double x[DT];
   KFn<DT>::load(x, Xs + (size_t)m * D, D);
-#pragma unroll
-  for (int j = 0; j < DT; j++) xs[j] = x[j] * s.inv_ls[j];
   // particle-scaled polynomial weights: L = o + sum_j (w_j x_j) y_j
   double xw1[DT], xw2a[DT], xw2b[DT];
 #pragma unroll
@@ -614,28 +637,13 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
   double E1a[DT], E1v[DT], C1a[DT], C1v[DT], C2a0[DT], C2v0[DT], C2a1[DT], C2v1[DT];
 #pragma unroll
   for (int j = 0; j < DT; j++) E1a[j] = E1v[j] = C1a[j] = C1v[j] = C2a0[j] = C2v0[j] = C2a1[j] = C2v1[j] = 0.0;
-  const double* v = V + (size_t)m * ldv;
   const int T = (N + RED_TILE - 1) / RED_TILE;
   constexpr int PER = RED_TILE / 32;
-  double vnext[PER];
   stage(0, 0);
-#pragma unroll
-  for (int it = 0; it < PER; it++) {
-    const int n = it * 32 + lane;
-    vnext[it] = n < N ? v[n] : 0.0;
-  }
   for (int t = 0; t < T; t++) {
     const int buf = t & 1;
-    double vcur[PER];
-#pragma unroll
-    for (int it = 0; it < PER; it++) vcur[it] = vnext[it];
     if (t + 1 < T) {
       stage(t + 1, buf ^ 1);
-#pragma unroll
-      for (int it = 0; it < PER; it++) {
-        const int n = (t + 1) * RED_TILE + it * 32 + lane;
-        vnext[it] = n < N ? v[n] : 0.0;  // V row prefetched one tile ahead (registers)
-      }
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -647,20 +655,13 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
       double y[DT];
 #pragma unroll
       for (int j = 0; j < DT; j++) y[j] = (j < D) ? sY[buf][j][i] : 0.0;
-      const double a = sA[buf][i], vn = vcur[it];  // both are zero past N: padded points contribute nothing
-      double d2 = 0.0;
-#pragma unroll
-      for (int j = 0; j < DT; j++) {
-        const double tt = fma(-y[j], s.inv_ls[j], xs[j]);
-        d2 = fma(tt, tt, d2);
-      }
-      const double ev = s.has_se ? s.lambda * exp(-d2) : 0.0;
-      double kv = ev, L2a = 0.0, L2b = 0.0;
+      const double a = sA[buf][i], vn = sV[buf][warp][i], kv = sK[buf][warp][i];  // all zero past N: padded points contribute nothing
+      double poly = 0.0, L2a = 0.0, L2b = 0.0;
       if (NP >= 1) {
         double L1 = s.poly_w2[0][0][MCP_MAX_D];
 #pragma unroll
         for (int j = 0; j < DT; j++) L1 = fma(xw1[j], y[j], L1);
-        kv += L1;
+        poly = L1;
       }
       if (NP >= 2) {
         L2a = s.poly_w2[1][0][MCP_MAX_D];
@@ -670,8 +671,9 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
           L2a = fma(xw2a[j], y[j], L2a);
           L2b = fma(xw2b[j], y[j], L2b);
         }
-        kv = fma(L2a, L2b, kv);
+        poly = fma(L2a, L2b, poly);
       }
+      const double ev = kv - poly;  // the squared-exponential part of k_n (exactly k_n when there is no polynomial term)
       mu = fma(a, kv, mu);
       q = fma(vn, kv, q);
       const double ta = a * ev, tv = vn * ev;
@@ -1019,8 +1021,12 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     double* jv = jac ? jvar + (size_t)m0 * E * g.spec.D : nullptr;
     if (jac && fast_reduce_ok(g.spec)) {
 #define MCP_FAST_REDUCE(DT_, NP_)                                                                                                   \
-  posterior_reduce_fast_kernel<DT_, NP_><<<cdiv(mc, RED_THREADS / 32), RED_THREADS, 0, st>>>(g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e,          \
-                                                               mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv)
+  do {                                                                                                                              \
+    static bool cfg_[MCP_MAX_DEVICES] = {};                                                                                         \
+    MCP_CUDA(ensure_dynamic_smem(cfg_, posterior_reduce_fast_kernel<DT_, NP_>, (int)red_smem_bytes<DT_>()));                        \
+    posterior_reduce_fast_kernel<DT_, NP_><<<cdiv(mc, RED_PB), RED_THREADS, red_smem_bytes<DT_>(), st>>>(                           \
+        g.spec, xs, mc, g.Xtr, g.alpha, N, Ks, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv);     \
+  } while (0)
       const int np_ = g.spec.n_poly;
       if (g.spec.D <= 4) { if (np_ == 0) MCP_FAST_REDUCE(4, 0); else if (np_ == 1) MCP_FAST_REDUCE(4, 1); else MCP_FAST_REDUCE(4, 2); }
       else if (g.spec.D <= 6) { if (np_ == 0) MCP_FAST_REDUCE(6, 0); else if (np_ == 1) MCP_FAST_REDUCE(6, 1); else MCP_FAST_REDUCE(6, 2); }
