@@ -79,6 +79,9 @@ typedef struct McpGp {
    * (no Jacobians) then form  w = K* L^-T  over the triangle only and  var = k** - |w|^2 : half the flops of K* Kinv.  NULL = not
    * available (e.g. Kinv came from a log file): the full product is used. */
   const double* Linv;        /* [N, ld_linv] or NULL */
+  /* max_n k(x_n, x_n) over the training inputs (INT8 variant only; 0 = unknown): with it the K* kernel bounds a row by
+   * |k(x, x_n)| <= sqrt(k(x,x) kdiag_max) and emits the row's digit planes itself instead of a second pass over K* */
+  double kdiag_max;
 } McpGp;
 
 /* ---- state -> gp-input map and integration (Model_learning.py:450-456,471-493,564-579,670-718) ---- */

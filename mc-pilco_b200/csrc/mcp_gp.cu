@@ -182,6 +182,109 @@ __global__ void __launch_bounds__(256) cov_fast_kernel(const __grid_constant__ M
   }
 }
 
+// K* tile kernel of the opt-in INT8 contraction: the same arithmetic per entry as cov_fast_kernel, but a thread owns FOUR consecutive
+// training points so that, besides the fp64 K* row (the reduce streams it), it emits the row's balanced base-256 digit planes as packed
+// 32-bit stores — the layout ozaki_slice_kernel writes (planes[row][seg][p][k], p = 0 most significant; mcp_ozaki.cu) — and K* is never
+// read back for slicing.  The row scale 2^e must be known before the first entry: it comes from the Cauchy-Schwarz bound
+// |k(x, x_n)| <= sqrt(k(x,x) max_n k(x_n,x_n)) instead of the exact row maximum (a few leading bits of 8 S are given away when the
+// bound is loose; the representation stays exact to 2^(e - 8 S)).
+template <int DT, int NP>
+__global__ void __launch_bounds__(256) cov_slice_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X1, int n1,
+                                                        const double* __restrict__ X2, int n2, double kdiag_max, double* __restrict__ K, int ldk,
+                                                        int S, int nseg, int Ks, int Ksp, int8_t* __restrict__ planes,
+                                                        int32_t* __restrict__ expo) {
+  __shared__ double sx[COV_ROWS][4][DT];  // per particle: x*ils, w1*x, w2a*x, w2b*x
+  __shared__ double sscale[COV_ROWS];     // 2^(8 S - e_row)
+  const int D = s.D, i0 = blockIdx.y * COV_ROWS, tid = threadIdx.x;
+  for (int el = tid; el < COV_ROWS * DT; el += 256) {
+    const int r = el / DT, j = el - r * DT;
+    const double xv = (i0 + r < n1 && j < D) ? X1[(size_t)(i0 + r) * D + j] : 0.0;
+    sx[r][0][j] = xv * s.inv_ls[j];
+    sx[r][1][j] = NP >= 1 ? xv * s.poly_w2[0][0][j] : 0.0;
+    sx[r][2][j] = NP >= 2 ? xv * s.poly_w2[1][0][j] : 0.0;
+    sx[r][3][j] = NP >= 2 ? xv * s.poly_w2[1][1][j] : 0.0;
+  }
+  if (tid < COV_ROWS) {
+    int ex = 0;
+    if (i0 + tid < n1) {
+      double x[DT];
+      KFn<DT>::load(x, X1 + (size_t)(i0 + tid) * D, D);
+      const double bound = sqrt(KFn<DT>::kdiag(s, x) * kdiag_max) * (1.0 + 1e-9);
+      ex = (bound > 0.0 && isfinite(bound)) ? max(ilogb(bound) + 3, -900) : 0;  // |k| 2^-e < 1/4 (see ozaki_slice_kernel)
+      if (blockIdx.x == 0) expo[i0 + tid] = ex;
+    }
+    sscale[tid] = scalbn(1.0, 8 * S - ex);
+  }
+  __syncthreads();
+  const int kk = (blockIdx.x * 256 + tid) * 4;  // first of this thread's four plane columns (Ksp is a multiple of 128)
+  if (kk >= nseg * Ksp) return;
+  const int seg = kk / Ksp, kq = kk - seg * Ksp, c0 = seg * Ks + kq;
+  double y[4][DT], ys[4][DT];
+  bool ok[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    ok[q] = kq + q < Ks && c0 + q < n2;
+#pragma unroll
+    for (int j = 0; j < DT; j++) {
+      y[q][j] = (ok[q] && j < D) ? X2[(size_t)(c0 + q) * D + j] : 0.0;
+      ys[q][j] = y[q][j] * s.inv_ls[j];
+    }
+  }
+  const int rows = min(COV_ROWS, n1 - i0);
+  const unsigned long long bias = S >= 8 ? 0x8080808080808080ull : ((1ull << (8 * S)) - 1ull) / 255ull * 128ull;
+  const size_t row_bytes = (size_t)nseg * S * Ksp;
+  for (int r = 0; r < rows; r++) {
+    double kv[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DT; j++) {
+        const double t = sx[r][0][j] - ys[q][j];
+        d2 = fma(t, t, d2);
+      }
+      double k = s.lambda * exp(-d2);
+      if (NP >= 1) {
+        double L1 = s.poly_w2[0][0][MCP_MAX_D];
+#pragma unroll
+        for (int j = 0; j < DT; j++) L1 = fma(sx[r][1][j], y[q][j], L1);
+        k += L1;
+      }
+      if (NP >= 2) {
+        double La = s.poly_w2[1][0][MCP_MAX_D], Lb = s.poly_w2[1][1][MCP_MAX_D];
+#pragma unroll
+        for (int j = 0; j < DT; j++) {
+          La = fma(sx[r][2][j], y[q][j], La);
+          Lb = fma(sx[r][3][j], y[q][j], Lb);
+        }
+        k = fma(La, Lb, k);
+      }
+      kv[q] = ok[q] ? k : 0.0;
+    }
+    // fp64 row (ldk is a multiple of 16 doubles and c0 of 4: 32-byte aligned); columns past n2 inside the padded row are zeros
+    if (c0 + 3 < ldk) {
+      double* out = K + (size_t)(i0 + r) * ldk + c0;
+      *reinterpret_cast<double2*>(out) = make_double2(kv[0], kv[1]);
+      *reinterpret_cast<double2*>(out + 2) = make_double2(kv[2], kv[3]);
+    }
+    const double sc = sscale[r];
+    unsigned long long G[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const long long F = isfinite(kv[q]) ? __double2ll_rn(kv[q] * sc) : 0;  // |F| < 2^(8S-2)
+      G[q] = ((unsigned long long)F + bias) ^ bias;
+    }
+    int8_t* prow = planes + (size_t)(i0 + r) * row_bytes + (size_t)seg * S * Ksp + kq;
+    for (int p = 0; p < S; p++) {
+      const int sh8 = 8 * (S - 1 - p);
+      unsigned packed = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) packed |= ((unsigned)(G[q] >> sh8) & 255u) << (8 * q);
+      *reinterpret_cast<unsigned*>(prow + (size_t)p * Ksp) = packed;
+    }
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256) kdiag_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ X, int n,
                                                     double* __restrict__ out) {
@@ -225,6 +328,26 @@ static int launch_cov(const McpGpSpec& s, const double* X1, int n1, const double
   }
   dim3 grid(cdiv(ncols_out, 32), cdiv(n1, 32));
   MCP_DISPATCH_D(s.D, (cov_kernel<DT><<<grid, 256, 0, st>>>(s, X1, n1, X2, n2, add_noise, K, ldk, ncols_out)));
+  MCP_LAUNCH_CHECK();
+  return MCP_OK;
+}
+
+// K* rows and their digit planes in one pass (INT8 variant; kernel shapes of the fast reduce only)
+void ozaki_geometry(int K, int S, int* nseg, int* Ks, int* Ksp);
+static int launch_cov_slice(const McpGpSpec& s, const double* X1, int n1, const double* X2, int n2, double kdiag_max, double* K, int ldk, int S,
+                            int8_t* planes, int32_t* expo, cudaStream_t st) {
+  if (n1 <= 0) return MCP_OK;
+  int nseg, Ks, Ksp;
+  ozaki_geometry(n2, S, &nseg, &Ks, &Ksp);
+  MCP_CHECK_ARG(ldk % 4 == 0 && ((uintptr_t)K % 32) == 0 && ((uintptr_t)planes % 4) == 0, "cov_slice: K* scratch must be 32-byte aligned");
+  MCP_CHECK_ARG(nseg * Ks >= ldk, "cov_slice: plane columns do not cover the K* row");  // nseg Ks is N rounded up to 128 per segment >= ld16(N)
+  dim3 grid(cdiv(nseg * Ksp, 1024), cdiv(n1, COV_ROWS));
+#define MCP_COV_SLICE(DT_, NP_) cov_slice_kernel<DT_, NP_><<<grid, 256, 0, st>>>(s, X1, n1, X2, n2, kdiag_max, K, ldk, S, nseg, Ks, Ksp, planes, expo)
+  const int np_ = s.n_poly;
+  if (s.D <= 4) { if (np_ == 0) MCP_COV_SLICE(4, 0); else if (np_ == 1) MCP_COV_SLICE(4, 1); else MCP_COV_SLICE(4, 2); }
+  else if (s.D <= 6) { if (np_ == 0) MCP_COV_SLICE(6, 0); else if (np_ == 1) MCP_COV_SLICE(6, 1); else MCP_COV_SLICE(6, 2); }
+  else { if (np_ == 0) MCP_COV_SLICE(8, 0); else MCP_COV_SLICE(8, 1); }
+#undef MCP_COV_SLICE
   MCP_LAUNCH_CHECK();
   return MCP_OK;
 }
@@ -910,6 +1033,9 @@ static inline int ld16(int n) { return (n + 15) / 16 * 16; }
 
 // opt-in INT8 tensor-core contraction (mcp_ozaki.cu)
 size_t ozaki_scratch_bytes(int mc, int N, int S);
+size_t ozaki_plane_bytes(int rows, int K, int S);
+int ozaki_mma(const int8_t* Ap, const int32_t* Ae, const int8_t* Bp, const int32_t* Be, int M, int N, int S, int nseg, int Ksp, double* V, int ldv,
+              cudaStream_t st);
 int ozaki_contract(const double* A, int lda, int mc, int N, int S, const int8_t* Bplanes, const int32_t* Bexp, double* V, int ldv, void* scratch,
                    size_t scratch_bytes, cudaStream_t st);
 
@@ -988,7 +1114,18 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
     double* Ks = scratch;
     double* V = scratch + (size_t)Mc * ldk;
     const double* xs = Xs + (size_t)m0 * g.spec.D;
-    if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
+    // INT8 variant with a kernel shape the fused K* kernel knows: the digit planes of K* come out of the K* kernel itself
+    const bool oz_fused = oz && fast_reduce_ok(g.spec) && g.kdiag_max > 0.0;
+    int8_t* oz_planes = nullptr;
+    int32_t* oz_exp = nullptr;
+    if (oz_fused) {
+      char* pz = (char*)align_up((size_t)(scratch + 2 * (size_t)Mc * ldk), 256);
+      oz_planes = (int8_t*)pz;
+      oz_exp = (int32_t*)(pz + align_up(ozaki_plane_bytes(mc, N, oz), 256));
+      if (int err = launch_cov_slice(g.spec, xs, mc, g.Xtr, N, g.kdiag_max, Ks, ldk, oz, oz_planes, oz_exp, st)) return err;
+    } else {
+      if (int err = launch_cov(g.spec, xs, mc, g.Xtr, N, 0, Ks, ldk, ldk, st)) return err;
+    }
     if (!jac && !oz && g.Linv != nullptr && dgemm_tma_usable(Ks, ldk, g.Linv, g.ld_linv, V, ldk)) {
       // forward-only: w = K* L^-T over the triangle (column tile n0 needs k < n0 + tile), var = k** - |w|^2: N^2 instead of 2 N^2 flops
       prof_begin(st);
@@ -1004,7 +1141,11 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
       continue;
     }
     prof_begin(st);
-    if (oz) {
+    if (oz_fused) {
+      int nseg_, Ks_, Ksp_;
+      ozaki_geometry(N, oz, &nseg_, &Ks_, &Ksp_);
+      if (int err = ozaki_mma(oz_planes, oz_exp, g.kinv_planes, g.kinv_exp, mc, N, oz, nseg_, Ksp_, V, ldk, st)) return err;
+    } else if (oz) {
       void* osc = (void*)(scratch + 2 * (size_t)Mc * ldk);
       const size_t osb = (scratch_doubles - 2 * (size_t)Mc * ldk) * sizeof(double);
       if (int err = ozaki_contract(Ks, ldk, mc, N, oz, g.kinv_planes, g.kinv_exp, V, ldk, osc, osb, st)) return err;

@@ -51,16 +51,18 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
         F[i] = isfinite(v) ? __double2ll_rn(scalbn(v, sh)) : 0;  // |F| < 2^(8S-2) <= 2^62
       }
     }
-#pragma unroll 1
-    for (int t = S - 1; t >= 0; t--) {
+    // balanced base-256 digits without a carry chain: F = sum_t d_t 256^t with d_t in [-128, 127]  <=>  F + sum_t 128 256^t has the
+    // plain bytes d_t + 128, and (byte ^ 0x80) is d_t as int8.  Plane p holds digit t = S-1-p (most significant digit in plane 0).
+    unsigned long long G[4];
+    const unsigned long long bias = S >= 8 ? 0x8080808080808080ull : ((1ull << (8 * S)) - 1ull) / 255ull * 128ull;
+#pragma unroll
+    for (int i = 0; i < 4; i++) G[i] = ((unsigned long long)F[i] + bias) ^ bias;
+    for (int p = 0; p < S; p++) {
+      const int sh8 = 8 * (S - 1 - p);
       unsigned packed = 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const long long d = ((F[i] + 128) & 255) - 128;  // balanced digit in [-128, 127]
-        F[i] = (F[i] - d) >> 8;
-        packed |= ((unsigned)d & 255u) << (8 * i);
-      }
-      *reinterpret_cast<unsigned*>(out + ((size_t)seg * S + (reverse ? S - 1 - t : t)) * Ksp + k) = packed;
+      for (int i = 0; i < 4; i++) packed |= ((unsigned)(G[i] >> sh8) & 255u) << (8 * i);
+      *reinterpret_cast<unsigned*>(out + ((size_t)seg * S + (reverse ? S - 1 - p : p)) * Ksp + k) = packed;
     }
   }
 }
@@ -85,6 +87,13 @@ static OzGeom ozaki_geom(int K, int S) {
 }
 
 // bytes of the digit planes of a [rows x K] matrix with S slices
+void ozaki_geometry(int K, int S, int* nseg, int* Ks, int* Ksp) {
+  const OzGeom g = ozaki_geom(K, S);
+  *nseg = g.nseg;
+  *Ks = g.Ks;
+  *Ksp = g.Ksp;
+}
+
 size_t ozaki_plane_bytes(int rows, int K, int S) {
   const OzGeom g = ozaki_geom(K, S);
   return (size_t)rows * g.nseg * S * g.Ksp;

@@ -22,7 +22,7 @@ class GpSpec(C.Structure):
 class Gp(C.Structure):
     _fields_ = [("spec", GpSpec), ("N", C.c_int32), ("ld_kinv", C.c_int32), ("Xtr", C.c_void_p), ("alpha", C.c_void_p),
                 ("Kinv", C.c_void_p), ("var_scale", C.c_double), ("kinv_planes", C.c_void_p), ("kinv_exp", C.c_void_p),
-                ("ozaki_slices", C.c_int32), ("ld_linv", C.c_int32), ("Linv", C.c_void_p)]
+                ("ozaki_slices", C.c_int32), ("ld_linv", C.c_int32), ("Linv", C.c_void_p), ("kdiag_max", C.c_double)]
 
 
 class Model(C.Structure):

@@ -215,6 +215,7 @@ class FittedGp:
         import os
         self.ozaki = int(os.environ.get("MCPILCO_OZAKI", "0")) if ozaki_slices is None else int(ozaki_slices)
         self.planes = self.plane_exp = None
+        self.kdiag_max = 0.0
         if self.ozaki:
             L = _enter(self.Xtr.device)
             if not L.mcpilco_ozaki_available():
@@ -225,6 +226,9 @@ class FittedGp:
             self.plane_exp = torch.empty(self.N, dtype=torch.int32, device=self.Xtr.device)
             N.check(L.mcpilco_ozaki_prepare(_ptr(self.Kinv), self.N, self.ld, self.ozaki, _ptr(self.planes), _ptr(self.plane_exp),
                                             _stream(self.Xtr.device)))
+            # bound for the rows of K* (Cauchy-Schwarz): lets the K* kernel choose the row scale and emit the digit planes itself
+            kd = gp_diag_covariance(spec, self.Xtr).max()
+            self.kdiag_max = float(kd) if bool(torch.isfinite(kd)) else 0.0
 
     def fill(self, g):
         C.memmove(C.byref(g.spec), C.byref(self.spec), C.sizeof(N.GpSpec))
@@ -235,6 +239,7 @@ class FittedGp:
         g.kinv_planes = self.planes.data_ptr() if self.planes is not None else None
         g.kinv_exp = self.plane_exp.data_ptr() if self.plane_exp is not None else None
         g.Linv, g.ld_linv = (self.Linv.data_ptr(), self.ld_linv) if self.Linv is not None else (None, 0)
+        g.kdiag_max = self.kdiag_max
 
 
 def _gp_array(gps):
