@@ -50,6 +50,10 @@ def parse():
                     help="opt-in INT8 tensor-core contraction with error compensation for the main measurement (default 0: native fp64)")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra timing of the opt-in INT8 contraction variants")
     ap.add_argument("--se-only", action="store_true", help="config 2 kernel (pure squared-exponential)")
+    ap.add_argument("--no-real-shapes", action="store_true", help="skip the block that times BASELINE configs 1-4 at their real sizes")
+    ap.add_argument("--no-forward-only", action="store_true", help="skip the forward-only (no-grad rollout) measurement")
+    ap.add_argument("--cpu-particles-all", type=int, default=2048, help="cpu_baseline sample with all host threads: particles (SURVEY 8d: min(M, 2048))")
+    ap.add_argument("--cpu-horizon-all", type=int, default=8, help="cpu_baseline sample with all host threads: horizon (SURVEY 8d: 8)")
     return ap.parse_args()
 
 
@@ -95,6 +99,20 @@ def cpu_rollout_sample(sc, M, H, threads, repeats, warmup, fitted=None):
     return times
 
 
+def cpu_fit(sc, threads):
+    """[(alpha, Kinv)] per output from the oracle's own fit (reference GP_prior.py:91-115,130-135)."""
+    from oracle import mcpilco_oracle as O
+    torch.set_num_threads(threads)
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+    out = []
+    for e, g in enumerate(sc["gps"]):
+        sp = O.make_spec(sc["D"], log_ls=g["log_ls"], log_lambda=float(np.log(g["lambda"])), mean=g["mean"],
+                         mpk_log_pars=[np.log(w) for w in g["mpk"]], sigma_n=g["sigma_n"])
+        alpha, _, Kinv = O.gp_fit(sp, T(sc["X"]), T(sc["Y"][:, e:e + 1]))
+        out.append((alpha, Kinv))
+    return out
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -110,14 +128,18 @@ def reference_arm(args):
     sc = W.cartpole_sweep(args.train_points, se_only=args.se_only)
     cores = host_cores()
     M, H = args.cpu_particles, args.cpu_horizon
-    times = cpu_rollout_sample(sc, M, H, cores, args.steps, args.warmup)
+    fitted = cpu_fit(sc, cores)  # the O(N^3) fit is outside the metric: once, with all threads
+    times = cpu_rollout_sample(sc, M, H, cores, args.steps, args.warmup, fitted=fitted)
     ms = 1e3 * float(np.sum(times))
     value = M * H * len(times) / float(np.sum(times))
     sample = "oracle port (torch CPU fp64 + autograd) of the same workload at M=%d particles x H=%d steps per step (memory ~ M*N*H*E forbids the full size), %d threads" % (M, H, cores)
+    t1 = cpu_rollout_sample(sc, min(256, M), H, 1, repeats=1, warmup=0, fitted=fitted)
+    one_thread = {"value": min(256, M) * H / float(np.sum(t1)), "unit": "particle-steps/s", "cores": 1,
+                  "sample": "same port with torch.set_num_threads(1), the reference's shipped setting (test_mcpilco_cartpole.py:46-47), M=%d x H=%d, one rollout" % (min(256, M), H)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / max(len(times), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
-            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample, "one_thread": one_thread},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -206,6 +228,82 @@ def build_objects(sc, dev):
     ml.gp_output_list = [T(sc["Y"][:, e:e + 1]) for e in range(sc["E"])]
     ml.dim_state, ml.dim_input, ml.num_samples = sc["Ds"], sc["Du"], sc["N"]
     return obj
+
+
+def real_shapes_block(dev, with_cpu):
+    """BASELINE configs 1-4 at the reference's real sizes (C1-C4; latency-bound, ~1 GFLOP per rollout): per config the GPU
+    time of one rollout forward + backward through the class API (CUDA events), the WALL time of one whole optimisation step of
+    reinforce_policy's inner sequence (zero_grad, apply_policy, cost, the reference's NaN host sync of MC_PILCO.py:497, backward,
+    torch Adam step) and, beside them, the oracle port of the reference on the host CPU (1 thread = the reference's shipped setting,
+    test_mcpilco_cartpole.py:46-47, and all threads) on the same synthetic scenario."""
+    from mcpilco_b200 import workloads as W
+    import contextlib
+    out = {}
+    for key in W.REAL_SHAPES:
+        sc = W.real_shape(key, with_noise=True)
+        with contextlib.redirect_stdout(sys.stderr):
+            obj = W.build_pilco(sc, dev)
+        params = [p for p in obj.control_policy.parameters() if p.requires_grad]
+        kw = W.apply_kwargs(sc, dev)
+        opt = torch.optim.Adam(params, lr=1e-3)
+
+        def fwd_bwd():
+            for p in params:
+                p.grad = None
+            st, inp = obj.apply_policy(**kw)
+            cost, _ = obj.cost_function(st, inp, 0)
+            cost.backward()
+            return cost
+
+        def opt_step():
+            opt.zero_grad(set_to_none=True)
+            st, inp = obj.apply_policy(**kw)
+            cost, _ = obj.cost_function(st, inp, 0)
+            nan = bool(torch.isnan(cost))  # the per-step host synchronisation the reference's loop has
+            cost.backward()
+            opt.step()
+            return nan
+
+        reps = 10 if key == "c4" else 30
+        for _ in range(3):
+            fwd_bwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            cost = fwd_bwd()
+        e1.record()
+        torch.cuda.synchronize()
+        gpu_ms = e0.elapsed_time(e1) / reps
+        for _ in range(3):
+            opt_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            opt_step()
+        torch.cuda.synchronize()
+        wall_ms = 1e3 * (time.perf_counter() - t0) / reps
+        row = {"N": sc["N"], "M": sc["M"], "H": sc["H"], "nb": sc["policy"]["nb"], "D": sc["D"], "E": sc["E"],
+               "gpu_ms_fwd_bwd": gpu_ms, "opt_step_wall_ms": wall_ms, "wall_over_gpu": wall_ms / gpu_ms,
+               "particle_steps_per_s": sc["M"] * sc["H"] / (gpu_ms * 1e-3), "cost": float(cost.detach())}
+        if with_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers as Hh  # the oracle port of the reference: the CPU baseline leg only
+            cores = host_cores()
+            for label, thr in (("cpu_ms_1thread", 1), ("cpu_ms_all_threads", cores)):
+                torch.set_num_threads(thr)
+                gps = Hh.oracle_fit(sc)
+                ts = []
+                for it in range(1 if key == "c4" and thr == 1 else 2):
+                    t0 = time.perf_counter()
+                    Hh.oracle_rollout(sc, gps)
+                    ts.append(time.perf_counter() - t0)
+                row[label] = 1e3 * ts[-1]
+            row["cpu_threads_all"] = cores
+            row["speedup_vs_cpu_1thread"] = row["cpu_ms_1thread"] / gpu_ms
+            row["speedup_vs_cpu_all_threads"] = row["cpu_ms_all_threads"] / gpu_ms
+        out[key] = row
+    return out
 
 
 def own_arm(args):
@@ -360,6 +458,35 @@ def own_arm(args):
         os.environ["MCPILCO_OZAKI"] = "0"
         ml._fitted_cache = None
 
+    # ---- forward-only rollout (no-grad: reference MC_PILCO.py:430-456, apply_mcpilco_policy_on_model.py:66-76): the contraction runs
+    #      over the triangular factor L^-1 (N^2 flops per particle-step and output instead of 2 N^2) ----
+    forward_only = None
+    if not args.no_forward_only:
+        def fwd_step():
+            with torch.no_grad():
+                st, inp = obj.apply_policy(particles_initial_state_mean=mean_d, particles_initial_state_var=var_d, **kw)
+                return obj.cost_function(st, inp, 0)[0]
+        fwd_step(); fwd_step()
+        barrier()
+        ops.prof_enable(True)
+        e0.record()
+        for _ in range(2):
+            fc = fwd_step()
+        e1.record()
+        barrier()
+        fms = max_over_ranks(e0.elapsed_time(e1)) / 2
+        f_ms, f_n, f_fl = ops.prof_read()
+        ops.prof_enable(False)
+        Ns_ = [g.N for g in ml.fitted_gps()]
+        Ff = W.flops_per_particle_step(Ns_, sc["D"], need_grad=False)
+        fval = M_global * H / (fms * 1e-3)
+        forward_only = {"value": fval, "unit": "particle-steps/s (rollout forward only)", "ms_per_step": fms, "cost": float(fc),
+                        "flops_per_particle_step": Ff, "step_frac_of_fp64_peak": Ff * fval / world * 1e-12 / FP64_PEAK_TFLOPS,
+                        "contraction": "w = K* L^-T over the triangle (dgemm_tma_kernel<TRIM>, heavy column tiles first), var = k** - |w|^2",
+                        "contraction_tflops": f_fl / (f_ms * 1e-3) * 1e-12 if f_ms > 0 else None,
+                        "contraction_frac_of_fp64_peak": f_fl / (f_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS if f_ms > 0 else None,
+                        "kernel_share_of_step": f_ms / (2 * fms) if f_ms > 0 else None}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -380,24 +507,39 @@ def own_arm(args):
             "dtype": "f64" if args.ozaki == 0 else "f64 results via int8 digit planes (Ozaki-%d)" % args.ozaki, "data": "synthetic",
             "config": dict(workload_config(args, world), precompute_ms=precompute_ms, precompute_cold_ms=precompute_cold_ms, cost=cost_v, e2e_steps=args.e2e_steps,
                            flops_per_particle_step=F, step_tflops_per_gpu=F * value / world * 1e-12,
-                           step_frac_of_fp64_peak=F * value / world * 1e-12 / FP64_PEAK_TFLOPS),
+                           step_frac_of_fp64_peak=F * value / world * 1e-12 / FP64_PEAK_TFLOPS,
+                           # a rollout of H states has H - 1 GP transitions: the same fraction counted per transition
+                           step_frac_of_fp64_peak_per_transition=F * value / world * 1e-12 / FP64_PEAK_TFLOPS * (H - 1) / H),
             "roofline": {"bound": "tensor", "kernel": ("dgemm_tma_kernel (V = K* Kinv, FP64 DMMA.8x8x4, TMA + mbarrier pipeline)" if args.ozaki == 0 else
                                                       "int8 tcgen05 plane GEMMs + slice/combine (fp64-equivalent flops)"), "achieved": achieved,
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": None if achieved is None else achieved / FP64_PEAK_TFLOPS,
-                         "traffic": traffic, "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                         "traffic": traffic,
+                         "traffic_source": "STATIC: dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture "
+                                           "(profiles/ncu_gemm_summary.json, M = N = 8192); not measured in this run — achieved/frac are live",
+                         "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                          "flops_per_launch": gemm_fl / max(gemm_n, 1), "kernel_share_of_step": gemm_ms / ms,
                          "peak_source": "own measurement on this pool (FP64 is absent from MEASURED_PEAKS.json): profiles/microbench/r01_fp64_peaks.txt"},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": None if ms_e2e is None else ms_e2e / args.e2e_steps},
-            "gpu_launches": launches, "clocks": clocks, "variants": variants}
+            "gpu_launches": launches, "clocks": clocks, "variants": variants, "forward_only": forward_only}
+    if world == 1 and not args.no_real_shapes:
+        line["real_shapes"] = real_shapes_block(dev, with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
+        # the sweep shape cannot be run by the reference at full size (memory ~ M N H E); all host threads at
+        # min(M, 2048) x H = 8, and the reference's shipped single-thread setting on a smaller sample, both per particle-step
         cores = host_cores()
         fitted = [(g.alpha.detach().cpu().reshape(-1, 1), g.Kinv.detach().cpu().contiguous()) for g in ml.fitted_gps()]
-        Mc, Hc = args.cpu_particles, args.cpu_horizon
-        times = cpu_rollout_sample(sc, Mc, Hc, cores, repeats=2, warmup=1, fitted=fitted)
-        line["cpu_baseline"] = {"value": Mc * Hc * len(times) / float(np.sum(times)), "unit": "particle-steps/s", "cores": cores, "kind": "port",
-                                "sample": "oracle port (torch CPU fp64 + autograd) of the same workload at M=%d x H=%d per rollout, 2 timed "
-                                          "rollouts after 1 warm-up, %d threads" % (Mc, Hc, cores)}
+        Ma, Ha = min(args.cpu_particles_all, args.particles_per_gpu), args.cpu_horizon_all
+        cpu_rollout_sample(sc, 128, 2, cores, repeats=1, warmup=0, fitted=fitted)  # thread pool / allocator warm-up
+        times = cpu_rollout_sample(sc, Ma, Ha, cores, repeats=1, warmup=0, fitted=fitted)
+        M1, H1 = min(256, args.cpu_particles), args.cpu_horizon
+        times1 = cpu_rollout_sample(sc, M1, H1, 1, repeats=1, warmup=0, fitted=fitted)
+        line["cpu_baseline"] = {"value": Ma * Ha * len(times) / float(np.sum(times)), "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                                "sample": "oracle port (torch CPU fp64 + autograd; /root/reference cannot travel to the GPU box) of the same workload at "
+                                          "M=%d x H=%d, one timed rollout after a small warm-up, %d threads" % (Ma, Ha, cores),
+                                "one_thread": {"value": M1 * H1 / float(np.sum(times1)), "unit": "particle-steps/s", "cores": 1,
+                                               "sample": "same port, torch.set_num_threads(1) (the reference's shipped setting, "
+                                                         "test_mcpilco_cartpole.py:46-47), M=%d x H=%d, one rollout" % (M1, H1)}}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -115,3 +115,78 @@ def flops_per_particle_step(N_list, D, need_grad=True):
     if need_grad:
         return float(sum(2.0 * n * n + (20.0 * D + 20.0) * n for n in N_list))
     return float(sum(1.0 * n * n + (10.0 * D + 10.0) * n for n in N_list))
+
+
+def build_pilco(sc, dev, pretrain=True):
+    """The reference's construction sequence (test_mcpilco_cartpole.py:49-231, test_mcpilco4pms_cartpole.py, test_mcpilco_ur5_mujoco.py:57-162)
+    against mcpilco_b200's classes for any scenario dict of this module / tests/scenarios.py: model-learning object with the scenario's
+    GP hyper-parameters and training set, policy, cost, MC_PILCO / MC_PILCO4PMS object.  Returns the MC_PILCO object."""
+    import contextlib
+    import sys
+
+    import torch
+
+    from .model_learning import Model_learning as ML
+    from .policy_learning import Cost_function as CF
+    from .policy_learning import MC_PILCO as MCP
+    from .policy_learning import Policy as PO
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device=dev)  # noqa: E731
+    D = sc["D"]
+    dicts = []
+    for g in sc["gps"]:
+        rbf = dict(active_dims=np.arange(D), lengthscales_init=np.exp(g["log_ls"]), flg_train_lengthscales=True, lambda_init=np.array([g["lambda"]]),
+                   flg_train_lambda=False, sigma_n_init=np.array([g["sigma_n"]]), flg_train_sigma_n=True, mean_init=np.array([g["mean"]]),
+                   sigma_n_num=None, dtype=torch.float64, device=dev)
+        if g["mpk"]:
+            mpk = dict(active_dims=np.arange(D), poly_deg=len(g["mpk"]), Sigma_pos_par_init_list=list(g["mpk"]),
+                       flg_train_Sigma_pos_par_list=[True] * len(g["mpk"]), dtype=torch.float64, device=dev)
+            dicts.append([rbf, mpk])
+        else:
+            dicts.append(rbf)
+    m, p, c = sc["model"], sc["policy"], sc["cost"]
+    if m["kind"] == "speed":
+        cls = ML.Speed_Model_learning_RBF_MPK_angle_state if sc["gps"][0]["mpk"] else ML.Speed_Model_learning_RBF_angle_state
+        ml = cls(num_gp=sc["E"], init_dict_list=dicts, T_sampling=m["T"], angle_indeces=m["angle"], not_angle_indeces=m["not_angle"],
+                 vel_indeces=m["vel"], not_vel_indeces=m["pos"], device=dev)
+    else:
+        ml = ML.Model_learning_RBF(num_gp=sc["E"], init_dict_list=dicts, device=dev)
+    ml.gp_inputs = T(sc["X"])
+    ml.gp_output_list = [T(sc["Y"][:, e:e + 1]) for e in range(sc["E"])]
+    ml.dim_state, ml.dim_input, ml.num_samples = sc["Ds"], sc["Du"], sc["N"]
+    if pretrain:
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
+            for e in range(sc["E"]):
+                ml.pretrain_gp(e)
+        ml.set_eval_mode()
+    pkw = dict(input_dim=sc["Du"], num_basis=p["nb"], lengthscales_init=p["lengthscales"], centers_init=p["centers"], weight_init=p["weight"],
+               flg_squash=p["u_max"] is not None, u_max=p["u_max"] if p["u_max"] is not None else 1, flg_drop=True, flg_bias=p["bias"] is not None,
+               bias_init=p["bias"], device=dev)
+    if p["kind"] == "angles":
+        pcls, pkw = PO.Sum_of_gaussians_with_angles, dict(pkw, state_dim=sc["Ds"], angle_indices=p["angle"], non_angle_indices=p["non_angle"])
+    elif p["kind"] == "target":
+        pcls, pkw = PO.Sum_of_gaussians_with_target_trajectory, dict(pkw, state_dim=2 * sc["Ds"], target_traj=p["target_traj"])
+    else:
+        pcls, pkw = PO.Sum_of_gaussians, dict(pkw, state_dim=sc["Ds"], scale_factor=p["scale"])
+    if c["kind"] == "cart_pole":
+        ccls, ckw = CF.Cart_pole_cost, dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), angle_index=c["angle_index"], pos_index=c["pos_index"])
+    elif c["kind"] == "sat_traj":
+        ccls, ckw = CF.Expected_saturated_distance_from_trajectory, dict(target_traj=T(c["target_traj"]), lengthscales=T(c["ls"]))
+    else:
+        ccls, ckw = CF.Expected_saturated_distance, dict(target_state=T(c["target"]), lengthscales=T(c["ls"]), active_dims=c["active"])
+    common = dict(T_sampling=m["T"] or 0.05, state_dim=sc["Ds"], input_dim=sc["Du"], f_sim=None, f_model_learning=lambda: ml, model_learning_par={},
+                  f_rand_exploration_policy=None, rand_exploration_policy_par=None, f_control_policy=pcls, control_policy_par=pkw,
+                  f_cost_function=ccls, cost_function_par=ckw, device=dev)
+    if "pms" in sc:
+        q = sc["pms"]
+        std = np.zeros(sc["Ds"])
+        std[list(q["pos_idx"])] = q["std_pos"]
+        return MCP.MC_PILCO4PMS(pos_indeces=q["pos_idx"], vel_indeces=q["vel_idx"], filtering_dict={"fc": q["fc"]}, std_meas_noise=std, **common)
+    return MCP.MC_PILCO(**common)
+
+
+def apply_kwargs(sc, dev, num_particles=None):
+    import torch
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device=dev)  # noqa: E731
+    return dict(particles_initial_state_mean=T(sc["x0_mean"]), particles_initial_state_var=T(sc["x0_var"]), flg_particles_init_uniform=False,
+                particles_init_up_bound=None, particles_init_low_bound=None, flg_particles_init_multi_gauss=False,
+                num_particles=int(num_particles or sc["M"]), T_control=sc["H"], p_dropout=sc["p_dropout"])
