@@ -283,9 +283,43 @@ def real_shapes_block(dev, with_cpu):
             opt_step()
         torch.cuda.synchronize()
         wall_ms = 1e3 * (time.perf_counter() - t0) / reps
+        # the same step with the rollout's forward + backward captured in a CUDA graph (what reinforce_policy runs)
+        import mcpilco_b200.policy_learning.MC_PILCO as MCP
+        graph_ms = graph_wall_ms = None
+        if MCP._GraphedRollout.eligible(obj):
+            obj._trial_index = 0
+            init = dict(kw)
+            p_drop = init.pop("p_dropout")
+            g = MCP._GraphedRollout(obj, init, p_drop)
+
+            def graph_step():
+                c, _ = g.replay()
+                nan = bool(torch.isnan(c))
+                g.deposit_grads()
+                opt.step()
+                return nan
+
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            graph_ms = e0.elapsed_time(e1) / reps
+            for _ in range(3):
+                graph_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                graph_step()
+            torch.cuda.synchronize()
+            graph_wall_ms = 1e3 * (time.perf_counter() - t0) / reps
         row = {"N": sc["N"], "M": sc["M"], "H": sc["H"], "nb": sc["policy"]["nb"], "D": sc["D"], "E": sc["E"],
                "gpu_ms_fwd_bwd": gpu_ms, "opt_step_wall_ms": wall_ms, "wall_over_gpu": wall_ms / gpu_ms,
-               "particle_steps_per_s": sc["M"] * sc["H"] / (gpu_ms * 1e-3), "cost": float(cost.detach())}
+               "graph_gpu_ms_fwd_bwd": graph_ms, "graph_opt_step_wall_ms": graph_wall_ms,
+               "particle_steps_per_s": sc["M"] * sc["H"] / ((graph_ms or gpu_ms) * 1e-3), "cost": float(cost.detach())}
         if with_cpu:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import helpers as Hh  # the oracle port of the reference: the CPU baseline leg only
@@ -300,8 +334,8 @@ def real_shapes_block(dev, with_cpu):
                     ts.append(time.perf_counter() - t0)
                 row[label] = 1e3 * ts[-1]
             row["cpu_threads_all"] = cores
-            row["speedup_vs_cpu_1thread"] = row["cpu_ms_1thread"] / gpu_ms
-            row["speedup_vs_cpu_all_threads"] = row["cpu_ms_all_threads"] / gpu_ms
+            row["speedup_vs_cpu_1thread"] = row["cpu_ms_1thread"] / (graph_ms or gpu_ms)
+            row["speedup_vs_cpu_all_threads"] = row["cpu_ms_all_threads"] / (graph_ms or gpu_ms)
         out[key] = row
     return out
 

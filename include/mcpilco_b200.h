@@ -151,6 +151,9 @@ typedef struct McpNoise {
   uint64_t seed;
   uint64_t particle_offset; /* global id of local particle 0 */
   double p_dropout;
+  /* optional DEVICE uint64 added to `seed` when the kernels run (wrapping): lets a CUDA graph that was captured once draw fresh
+   * noise on every replay — the host bumps the device word, the baked kernel arguments stay.  NULL = not used. */
+  const uint64_t* seed_dev;
 } McpNoise;
 
 /* ---- one rollout (MC_PILCO.apply_policy, policy_learning/MC_PILCO.py:615-674 / :808-906) ---------- */
@@ -259,9 +262,9 @@ int mcpilco_policy_forward(const McpPolicy* policy, int M, int t, const double* 
 /* Initial particles (MC_PILCO.apply_policy, policy_learning/MC_PILCO.py:635-657) from counter-based Philox keyed by the
  * global particle id:  kind 0: x0 = a[k] + b[k] * n, n ~ N(0, I)  (a = mean, b = sqrt(var); n_modes > 1 draws the mode k
  * uniformly per particle: the multi-modal Gaussian of :640-647);  kind 1: x0 = a + (b - a) * u, u ~ U(0,1) (a = low, b = up
- * bound, :635-639).  a, b are DEVICE arrays [n_modes, Ds]. */
+ * bound, :635-639).  a, b are DEVICE arrays [n_modes, Ds]; seed_dev as in McpNoise (NULL = unused). */
 int mcpilco_init_particles(int kind, const double* a, const double* b, int n_modes, int M, int Ds, uint64_t seed,
-                           uint64_t particle_offset, double* x0, void* stream);
+                           uint64_t particle_offset, const uint64_t* seed_dev, double* x0, void* stream);
 
 /* Timing hook for bench.py's roofline: when enabled, every launch of the dominant kernel (the FP64 tensor-core GEMM
  * V = K* Kinv of the posterior) is bracketed by CUDA events on the launching stream.  read() synchronises those events and

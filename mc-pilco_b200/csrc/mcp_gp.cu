@@ -1062,10 +1062,8 @@ size_t gp_posterior_batched_doubles(int M, int E, int nmax) {
 int gp_posterior_batched_setup(const McpGp* gps, int E, int M, int nmax, double* scratch, size_t scratch_doubles, const McpGpDev** tab_out,
                                double** ks_out, cudaStream_t st) {
   MCP_CHECK_ARG(scratch_doubles >= gp_posterior_batched_doubles(M, E, nmax), "rollout (batched step): workspace too small");
-  McpGpDev host_tab[MCP_MAX_E];
-  gpdev_fill(host_tab, gps, E);
   McpGpDev* tab = reinterpret_cast<McpGpDev*>(scratch);
-  MCP_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(McpGpDev) * (size_t)E, cudaMemcpyHostToDevice, st));
+  MCP_CUDA(gpdev_upload(tab, gps, E, st));
   double* Ks = scratch + (sizeof(McpGpDev) * (size_t)E + 7) / 8 + 8;
   *ks_out = reinterpret_cast<double*>(align_up((size_t)Ks, 256));
   *tab_out = tab;

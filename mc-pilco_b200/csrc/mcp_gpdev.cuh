@@ -27,6 +27,17 @@ static inline void gpdev_fill(McpGpDev* host_tab, const McpGp* gps, int E) {
   }
 }
 
+// Upload of the table: one tiny kernel per GP that takes the descriptor BY VALUE (a kernel parameter is copied when the launch is
+// recorded), instead of an asynchronous host -> device copy from a host stack array — the copy would not survive stream capture into
+// a CUDA graph (the graph would re-read a dead stack frame on replay), the kernel does.
+__global__ void gpdev_store_kernel(const __grid_constant__ McpGpDev g, McpGpDev* __restrict__ dst);
+static inline cudaError_t gpdev_upload(McpGpDev* dev_tab, const McpGp* gps, int E, cudaStream_t st) {
+  McpGpDev host_tab[MCP_MAX_E];
+  gpdev_fill(host_tab, gps, E);
+  for (int e = 0; e < E; e++) gpdev_store_kernel<<<1, 32, 0, st>>>(host_tab[e], dev_tab + e);
+  return cudaGetLastError();
+}
+
 // Programmatic dependent launch (sm_90+): a kernel launched with programmatic stream serialisation may start while its predecessor
 // drains; it must wait here before touching anything the predecessor wrote.  A no-op without the launch attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
     double mu = mean[(size_t)m * E + e], v = var[(size_t)m * E + e];
     double delta = mu, coef = 0.0;
     if (mdl.particle_pred) {
-      double eps = nz.eps ? nz.eps[((size_t)t * M + m) * E + e] : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_EPS, e);
+      double eps = nz.eps ? nz.eps[((size_t)t * M + m) * E + e] : rng_normal(noise_seed(nz), nz.particle_offset + (uint64_t)m, t, RNG_EPS, e);
       double sd = sqrt(v);
       delta = fma(sd, eps, mu);
       coef = eps / (2.0 * sd);
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
     for (int i = 0; i < ms.n_pos; i++) {
       int ip = ms.pos_idx[i], iv = ms.vel_idx[i];
       double e = nz.meas_eps ? nz.meas_eps[((size_t)t * M + m) * ms.n_pos + i]
-                             : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_MEAS, i);
+                             : rng_normal(noise_seed(nz), nz.particle_offset + (uint64_t)m, t, RNG_MEAS, i);
       double np_old = pp[ip], mv_old = pp[iv];
       double np_new = fma(ms.std_pos[i], e, xn[ip]);
       double nv_old = nv[(size_t)m * ms.n_pos + i];
@@ -225,9 +225,10 @@ __global__ void __launch_bounds__(128) integrate_kernel(const __grid_constant__ 
 
 // initial particles from Philox (MC_PILCO.py:635-657); stream RNG_X0, "time" index 0
 __global__ void init_particles_kernel(int kind, const double* __restrict__ a, const double* __restrict__ b, int n_modes, int M, int Ds,
-                                      uint64_t seed, uint64_t offset, double* __restrict__ x0) {
+                                      uint64_t seed, uint64_t offset, const uint64_t* __restrict__ seed_dev, double* __restrict__ x0) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
+  if (seed_dev) seed += __ldg(seed_dev);
   uint64_t pid = offset + (uint64_t)m;
   int k = 0;
   if (n_modes > 1) {
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256) integrate_warp_kernel(const __grid_consta
     const double mu = mean[(size_t)m * E + lane], v = var[(size_t)m * E + lane];
     delta = mu;
     if (mdl.particle_pred) {
-      const double eps = nz.eps ? nz.eps[((size_t)t * M + m) * E + lane] : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_EPS, lane);
+      const double eps = nz.eps ? nz.eps[((size_t)t * M + m) * E + lane] : rng_normal(noise_seed(nz), nz.particle_offset + (uint64_t)m, t, RNG_EPS, lane);
       const double sd = sqrt(v);
       delta = fma(sd, eps, mu);
       coef = eps / (2.0 * sd);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(256) integrate_warp_kernel(const __grid_consta
     if (lane < ms.n_pos) {
       const int i = lane, ip = ms.pos_idx[i], iv = ms.vel_idx[i];
       const double e = nz.meas_eps ? nz.meas_eps[((size_t)t * M + m) * ms.n_pos + i]
-                                   : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, t, RNG_MEAS, i);
+                                   : rng_normal(noise_seed(nz), nz.particle_offset + (uint64_t)m, t, RNG_MEAS, i);
       const double np_old = pp[ip], mv_old = pp[iv];
       const double np_new = fma(ms.std_pos[i], e, xn[ip]);
       const double nv_old = nv[(size_t)m * ms.n_pos + i];
@@ -864,12 +865,13 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_policy_forward(con
 }
 
 extern "C" __attribute__((visibility("default"))) int mcpilco_init_particles(int kind, const double* a, const double* b, int n_modes, int M, int Ds,
-                                                                              uint64_t seed, uint64_t particle_offset, double* x0, void* stream) {
+                                                                              uint64_t seed, uint64_t particle_offset, const uint64_t* seed_dev, double* x0,
+                                                                              void* stream) {
   MCP_CHECK_ARG((kind == 0 || kind == 1) && a && b && n_modes >= 1 && M >= 0 && Ds >= 1 && Ds <= MCP_MAX_DS && (kind == 0 || n_modes == 1),
                 "init_particles: bad arguments (kind=%d n_modes=%d M=%d Ds=%d)", kind, n_modes, M, Ds);
   if (M == 0) return MCP_OK;
   MCP_CHECK_ARG(x0 != nullptr, "init_particles: null output");
-  init_particles_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(kind, a, b, n_modes, M, Ds, seed, particle_offset, x0);
+  init_particles_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(kind, a, b, n_modes, M, Ds, seed, particle_offset, seed_dev, x0);
   MCP_LAUNCH_CHECK();
   return MCP_OK;
 }

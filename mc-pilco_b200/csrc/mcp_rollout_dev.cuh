@@ -22,12 +22,15 @@ __device__ __forceinline__ double policy_feature(const McpPolicy& p, const doubl
   return f * p.inv_scale[j];
 }
 
+// Philox key of this rollout: the baked seed plus (optionally) a device word the host bumps between replays of a captured graph
+__device__ __forceinline__ uint64_t noise_seed(const McpNoise& nz) { return nz.seed_dev ? nz.seed + __ldg(nz.seed_dev) : nz.seed; }
+
 __device__ __forceinline__ bool dropout_active(const McpPolicy& p, const McpNoise& nz) { return p.use_drop && nz.p_dropout > 0.0; }
 
 // tm addresses the injected mask tensor, t the Philox counter (they differ only for the stand-alone policy call)
 __device__ __forceinline__ bool keep_unit(const McpNoise& nz, int M, int nb, int tm, int t, int m, int b) {
   if (nz.masks) return nz.masks[((size_t)tm * M + m) * nb + b] != 0;
-  return rng_keep(nz.seed, nz.particle_offset + (uint64_t)m, t, b, nz.p_dropout);
+  return rng_keep(noise_seed(nz), nz.particle_offset + (uint64_t)m, t, b, nz.p_dropout);
 }
 
 __device__ __forceinline__ double cost_value(const McpCost& c, const double* __restrict__ x, int t, int Ds) {

@@ -21,6 +21,13 @@
 
 namespace mcp {
 
+__global__ void gpdev_store_kernel(const __grid_constant__ McpGpDev g, McpGpDev* __restrict__ dst) {
+  const int n = (int)(sizeof(McpGpDev) / 8);  // the struct is a multiple of 8 bytes (doubles and pointers)
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&g);
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(dst);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = src[i];
+}
+
 // Programmatic dependent launch: the two kernels of a step are launched with programmatic stream serialisation, so the next grid's
 // launch latency overlaps the tail of the current one.  Every kernel of the chain first waits for its predecessor to complete and
 // flush (pdl_wait; a no-op without the launch attribute).  The successor is released implicitly when the blocks exit: an explicit
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(SS_THREADS, 3) small_step_kernel(const __grid_
         const double mu = s_mean[lane], v = s_var[lane];
         delta = mu;
         if (mdl.particle_pred) {
-          const double eps = nz.eps ? nz.eps[((size_t)tp * M + m) * E + lane] : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, tp, RNG_EPS, lane);
+          const double eps = nz.eps ? nz.eps[((size_t)tp * M + m) * E + lane] : rng_normal(noise_seed(nz), nz.particle_offset + (uint64_t)m, tp, RNG_EPS, lane);
           const double sd = sqrt(v);
           delta = fma(sd, eps, mu);
           coef = eps / (2.0 * sd);
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(SS_THREADS, 3) small_step_kernel(const __grid_
         for (int i = 0; i < ms.n_pos; i++) {
           const int ip = ms.pos_idx[i], iv = ms.vel_idx[i];
           const double e = nz.meas_eps ? nz.meas_eps[((size_t)tp * M + m) * ms.n_pos + i]
-                                       : rng_normal(nz.seed, nz.particle_offset + (uint64_t)m, tp, RNG_MEAS, i);
+                                       : rng_normal(noise_seed(nz), nz.particle_offset + (uint64_t)m, tp, RNG_MEAS, i);
           const double xp = __shfl_sync(0xffffffffu, xnew, ip);
           const double np_new = fma(ms.std_pos[i], e, xp);
           const double nv_old = nv[(size_t)m * ms.n_pos + i];
@@ -424,13 +431,11 @@ int rollout_fwd_small(const McpRollout* r, double* Xs, double* nv, double* scrat
   MCP_CHECK_ARG(scratch_doubles >= small_path_doubles(M, E, nmax), "rollout (small path): workspace too small");
   const int ldk = (nmax + 15) / 16 * 16;
   const size_t gp_stride = (size_t)M * ldk;
-  McpGpDev host_tab[MCP_MAX_E];
-  gpdev_fill(host_tab, r->gps, E);
   McpGpDev* tab = reinterpret_cast<McpGpDev*>(scratch);
   double* Ks = scratch + (sizeof(McpGpDev) * (size_t)E + 7) / 8 + 8;
   Ks = reinterpret_cast<double*>(align_up((size_t)Ks, 256));
   double* V = Ks + (size_t)E * gp_stride;
-  MCP_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(McpGpDev) * (size_t)E, cudaMemcpyHostToDevice, st));
+  MCP_CUDA(gpdev_upload(tab, r->gps, E, st));
   const int np = r->gps[0].spec.n_poly;
   const bool jac = r->need_grad != 0;
   const bool pdl = pdl_enabled();

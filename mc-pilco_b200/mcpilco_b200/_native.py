@@ -53,7 +53,7 @@ class Meas(C.Structure):
 
 class Noise(C.Structure):
     _fields_ = [("eps", C.c_void_p), ("masks", C.c_void_p), ("meas_eps", C.c_void_p), ("seed", C.c_uint64),
-                ("particle_offset", C.c_uint64), ("p_dropout", C.c_double)]
+                ("particle_offset", C.c_uint64), ("p_dropout", C.c_double), ("seed_dev", C.c_void_p)]
 
 
 class Rollout(C.Structure):
@@ -95,7 +95,7 @@ SYMBOLS = {
     "mcpilco_policy_forward": (C.c_int, [C.POINTER(Policy), C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_uint64, C.c_uint64,
                                          C.c_void_p, C.c_void_p]),
     "mcpilco_init_particles": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
-                                         C.c_void_p]),
+                                         C.c_void_p, C.c_void_p]),
     "mcpilco_ozaki_available": (C.c_int, []),
     "mcpilco_ozaki_plane_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mcpilco_ozaki_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -230,6 +230,15 @@ class FittedGp:
             kd = gp_diag_covariance(spec, self.Xtr).max()
             self.kdiag_max = float(kd) if bool(torch.isfinite(kd)) else 0.0
 
+    @classmethod
+    def from_parts(cls, spec, Xtr, alpha, Kinv, ld, var_scale, ozaki, planes, plane_exp, Linv, ld_linv, kdiag_max):
+        """Re-assemble a FittedGp from tensors that already passed __init__ (the torch.library op layer ships them as flat arguments);
+        no validation, no copies, no re-slicing of K^-1."""
+        g = cls.__new__(cls)
+        g.spec, g.Xtr, g.alpha, g.Kinv, g.ld, g.var_scale, g.N = spec, Xtr, alpha, Kinv, int(ld), float(var_scale), Xtr.shape[0]
+        g.ozaki, g.planes, g.plane_exp, g.Linv, g.ld_linv, g.kdiag_max = int(ozaki), planes, plane_exp, Linv, int(ld_linv), float(kdiag_max)
+        return g
+
     def fill(self, g):
         C.memmove(C.byref(g.spec), C.byref(self.spec), C.sizeof(N.GpSpec))
         g.N, g.ld_kinv = self.N, self.ld
@@ -288,7 +297,10 @@ class RolloutPlan:
 
     @_restores_device
     def __init__(self, model, gps, policy, pol_tensors, cost=None, cost_traj=None, meas=None, M=1, H=1, p_dropout=0.0,
-                 seed=0, particle_offset=0, need_grad=False, eps=None, masks=None, meas_eps=None, device=None, M_global=0):
+                 seed=0, particle_offset=0, need_grad=False, eps=None, masks=None, meas_eps=None, device=None, M_global=0, seed_dev=None,
+                 buffers=None):
+        """buffers: optional {"states", "inputs", "jac", "pol_in"} of an earlier forward pass to adopt instead of allocating (the
+        backward op of the torch.library layer rebuilds a plan around the trajectories autograd saved)."""
         self.dev = device or gps[0].Xtr.device
         self.L = _enter(self.dev)
         self.gps = list(gps)
@@ -316,10 +328,20 @@ class RolloutPlan:
         if self.masks is not None and (not self.masks.is_cuda or tuple(self.masks.shape) != (H, M, policy.nb)):
             raise RuntimeError("rollout: masks must be a CUDA tensor [H, M, nb]")
         dev = self.dev
-        self.states = torch.empty(H, M, Ds, dtype=F64, device=dev)
-        self.inputs = torch.empty(H, M, Du, dtype=F64, device=dev)
-        self.jac = torch.empty(max(H - 1, 1), M, E, D, dtype=F64, device=dev) if need_grad else None
-        self.pol_in = torch.empty(H, M, Ds, dtype=F64, device=dev) if self.meas.enabled else None
+        bf = buffers or {}
+
+        def buf(name, shape):
+            t = bf.get(name)
+            if t is None:
+                return torch.empty(*shape, dtype=F64, device=dev)
+            if tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+                raise RuntimeError("rollout: adopted buffer %s must be contiguous %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+            return _need_cuda(t, name)
+
+        self.states = buf("states", (H, M, Ds))
+        self.inputs = buf("inputs", (H, M, Du))
+        self.jac = buf("jac", (max(H - 1, 1), M, E, D)) if need_grad else None
+        self.pol_in = buf("pol_in", (H, M, Ds)) if self.meas.enabled else None
         fused = self.cost.kind != 0
         self.costs = torch.empty(H, M, dtype=F64, device=dev) if fused else None
         self.cost_out = torch.empty(2, dtype=F64, device=dev) if fused else None
@@ -331,6 +353,8 @@ class RolloutPlan:
         r.M, r.H, r.need_grad, r.M_global = self.M, self.H, 1 if need_grad else 0, int(M_global)
         r.model, r.policy, r.cost, r.meas = model, policy, self.cost, self.meas
         r.noise.seed, r.noise.particle_offset, r.noise.p_dropout = int(seed), int(particle_offset), float(p_dropout)
+        self.seed_dev = seed_dev  # optional device int64/uint64 word added to the seed at run time (graph replays)
+        r.noise.seed_dev = seed_dev.data_ptr() if seed_dev is not None else None
         r.noise.eps = self.eps.data_ptr() if self.eps is not None else None
         r.noise.masks = self.masks.data_ptr() if self.masks is not None else None
         r.noise.meas_eps = self.meas_eps.data_ptr() if self.meas_eps is not None else None
@@ -418,14 +442,14 @@ def policy_forward(pst, tens, x, t=0, p_dropout=0.0, masks_t=None, seed=0, parti
 
 
 @_restores_device
-def init_particles(kind, a, b, M, seed=0, particle_offset=0):
+def init_particles(kind, a, b, M, seed=0, particle_offset=0, seed_dev=None):
     """Initial particles keyed by the global particle id.  kind "gauss": a = mean(s) [n_modes, Ds], b = std(s);
     kind "uniform": a = lower, b = upper bound.  MC_PILCO.py:635-657."""
     a, b = _c(a, "a").reshape(-1, a.shape[-1]), _c(b, "b").reshape(-1, b.shape[-1])
     L = _enter(a.device)
     x0 = torch.empty(int(M), a.shape[1], dtype=F64, device=a.device)
     N.check(L.mcpilco_init_particles(0 if kind == "gauss" else 1, _ptr(a), _ptr(b), a.shape[0], int(M), a.shape[1], int(seed),
-                                     int(particle_offset), _ptr(x0), _stream(a.device)))
+                                     int(particle_offset), _ptr(seed_dev), _ptr(x0), _stream(a.device)))
     return x0
 
 

@@ -24,48 +24,49 @@ from .. import distributed as D
 
 class _ParticleRollout(torch.autograd.Function):
     """states, inputs, cost, std_cost = rollout(policy parameters).  The graph of the reference (~H*E*40 nodes retaining
-    [M, N] tensors, MC_PILCO.py:522) collapses into this single node with O(M*H*E*D) checkpoints."""
+    [M, N] tensors, MC_PILCO.py:522) collapses into this single node with O(M*H*E*D) checkpoints.  It sits on the two torch.library
+    operators `torch.ops.mcpilco.rollout_fwd` / `rollout_bwd` (torch_ops.RolloutCall)."""
 
     @staticmethod
-    def forward(ctx, plan, x0, shard, *params):
-        states, inputs = plan.forward(x0)
-        # the node keeps the trajectories alive for the backward kernel through autograd's saved-output mechanism; the plan drops its
-        # own references so that  states -> fused-cost attribute -> cost -> this node -> plan -> states  is not a reference cycle
-        # (a cycle would keep every rollout's buffers alive until Python's cyclic GC runs)
-        ctx.save_for_backward(states, inputs)
-        plan.states = plan.inputs = None
-        ctx.plan, ctx.shard = plan, shard
+    def forward(ctx, call, need_grad, x0, shard, *params):
+        states, inputs, cost_out, cost_stats, jac, pol_in = call.forward(x0, need_grad)
+        # the trajectories and checkpoints the backward kernel needs travel through autograd's saved-tensor mechanism
+        ctx.save_for_backward(states, inputs, jac, pol_in, x0.detach())
+        ctx.call, ctx.shard, ctx.need_grad = call, shard, bool(need_grad)
         ctx.want_gx0 = bool(x0.requires_grad)
         ctx.n_params = len(params)
         ctx.set_materialize_grads(False)
         rank, world, group, m_global = shard
-        if plan.cost_out is None:
+        if cost_out is None:
             cost = std = torch.zeros((), dtype=states.dtype, device=states.device)
         elif world == 1:
-            cost, std = plan.cost_out[0].clone(), plan.cost_out[1].clone()
+            cost, std = cost_out[0].clone(), cost_out[1].clone()
         else:
             counts = [D.shard(m_global, r, world)[1] for r in range(world)]
-            mean, m2 = D.merge_cost_stats(D.gather_cost_stats(plan.cost_stats, group, world), counts)
+            mean, m2 = D.merge_cost_stats(D.gather_cost_stats(cost_stats, group, world), counts)
             cost, std = D.expected_cost_from_stats(mean, m2, m_global)
         ctx.mark_non_differentiable(std)
         return states, inputs, cost, std
 
     @staticmethod
     def backward(ctx, g_states, g_inputs, g_cost, g_std):
-        plan = ctx.plan
+        call = ctx.call
+        if not ctx.need_grad:
+            raise RuntimeError("rollout backward: the forward pass was run without need_grad")
+        states, inputs, jac, pol_in, x0 = ctx.saved_tensors
         rank, world, group, m_global = ctx.shard
-        w_local = plan.M / float(m_global)  # this shard's weight in the global particle mean
+        w_local = call.M / float(m_global)  # this shard's weight in the global particle mean
         generic = g_states is not None or g_inputs is not None
         if generic:
             # g_states / g_inputs are d loss / d (this shard's trajectories) of the GLOBAL loss: Expected_cost weights its local
             # particle mean by w_local itself when sharded; the fused cost's share (if the loss also uses it) is added in the kernel
-            gc = 0.0 if g_cost is None or plan.cost_out is None else float(g_cost) * w_local
-            gr = plan.backward(grad_cost=gc, grad_states=g_states, grad_inputs=g_inputs, want_gx0=ctx.want_gx0)
+            gc = 0.0 if g_cost is None or not call.has_cost else float(g_cost) * w_local
+            gr = call.backward(x0, states, inputs, jac, pol_in, grad_cost=gc, grad_states=g_states, grad_inputs=g_inputs, want_gx0=ctx.want_gx0)
             scale = None
         else:
             if g_cost is None:
-                return (None,) * (3 + ctx.n_params)
-            gr = plan.backward(grad_cost=w_local, want_gx0=ctx.want_gx0)
+                return (None,) * (4 + ctx.n_params)
+            gr = call.backward(x0, states, inputs, jac, pol_in, grad_cost=w_local, want_gx0=ctx.want_gx0)
             scale = g_cost  # stays on the device: no host sync
         keys = ["log_ls", "centers", "W"] + (["bias"] if ctx.n_params == 4 else [])
         if world > 1:
@@ -80,7 +81,91 @@ class _ParticleRollout(torch.autograd.Function):
         gx0 = gr["x0"] if ctx.want_gx0 else None
         if gx0 is not None and scale is not None:
             gx0 = gx0 * scale
-        return (None, gx0, None) + tuple(out)
+        return (None, None, gx0, None) + tuple(out)
+
+
+GOLDEN = 0x9E3779B97F4A7C15  # rollout counter -> Philox key stride
+MASK64 = (1 << 64) - 1
+
+
+class _GraphedRollout:
+    """One particle rollout forward + hand-written backward, captured ONCE in a CUDA graph and replayed per optimisation step
+    (the reference's step is MC_PILCO.py:484-522).  At the real configuration sizes a rollout is ~130-600 dependent
+    kernel launches of a few microseconds each: enqueueing them from Python costs more than running them, so the host — not the GPU
+    — bounds the optimisation step.  A replay is one cudaGraphLaunch.  What stays on the host is exactly what the reference's loop
+    does per step: the NaN test of the cost (its one synchronisation), the monitors and the torch optimiser step.
+
+    Fresh noise per replay without re-capturing: the kernels add a device word to the baked Philox seed (McpNoise.seed_dev); the host
+    sets it to GOLDEN * rollout_counter before each replay, which reproduces the key sequence of the un-graphed path bit for bit."""
+
+    def __init__(self, pilco, init, p_dropout):
+        self.pilco = pilco
+        dev = pilco.device
+        pol = pilco.control_policy
+        self.params = [pol.log_lengthscales, pol.centers, pol.f_linear.weight] + ([pol.f_linear.bias] if pol.flg_bias else [])
+        self.keys = ["log_ls", "centers", "W"] + (["bias"] if pol.flg_bias else [])
+        self.signature = self.signature_of(pilco, init, p_dropout)
+        as_dev = lambda v: None if v is None else torch.as_tensor(v, dtype=pilco.dtype, device=dev).clone()  # noqa: E731
+        # everything that would be a host -> device copy inside the captured region is staged here
+        self.init = dict(init)
+        for k in ("particles_initial_state_mean", "particles_initial_state_var", "particles_init_up_bound", "particles_init_low_bound"):
+            self.init[k] = as_dev(init[k])
+        self.p_dropout = float(p_dropout)
+        self.ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        if pilco._seed_base is None:
+            pilco._next_seed()
+            pilco._rollouts -= 1
+        self.base = pilco._seed_base & MASK64
+        # eager pass on the capture stream first: first-use initialisation of the native side (kernel attributes, the side streams and
+        # scratch that are keyed by the launching stream) must not happen inside the captured region
+        self.stream = torch.cuda.Stream(dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            self._run()
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.states, self.inputs, self.cost_out, self.grads = self._run()
+
+    @staticmethod
+    def signature_of(pilco, init, p_dropout):
+        pol, ml = pilco.control_policy, pilco.model_learning
+        params = [pol.log_lengthscales, pol.centers, pol.f_linear.weight] + ([pol.f_linear.bias] if pol.flg_bias else [])
+        return (float(p_dropout), int(init["num_particles"]), int(init["T_control"]), bool(init["flg_particles_init_uniform"]),
+                bool(init["flg_particles_init_multi_gauss"]), tuple(p.data_ptr() for p in params), id(ml.fitted_gps()), pilco._trial_index,
+                id(pilco.cost_function))
+
+    @staticmethod
+    def eligible(pilco):
+        import os
+        if os.environ.get("MCPILCO_NO_GRAPH", "0") == "1" or D.world()[1] > 1 or not torch.is_grad_enabled():
+            return False
+        cf = pilco.cost_function
+        return hasattr(cf, "fused_spec") and cf.fused_spec(pilco.state_dim, 2, pilco._trial_index) is not None
+
+    def _run(self):
+        p, i = self.pilco, self.init
+        H, M = int(i["T_control"]), int(i["num_particles"])
+        x0 = p._initial_particles(i["particles_initial_state_mean"], i["particles_initial_state_var"], i["flg_particles_init_uniform"],
+                                  i["particles_init_up_bound"], i["particles_init_low_bound"], i["flg_particles_init_multi_gauss"], M, 0,
+                                  self.base, None, seed_dev=self.ctr)
+        call = p._rollout_call(x0, M, 0, H, self.p_dropout, self.base, None, M, seed_dev=self.ctr)
+        states, inputs, cost_out, _, jac, pol_in = call.forward(x0, True)
+        grads = call.backward(x0, states, inputs, jac, pol_in, grad_cost=1.0)
+        return states, inputs, cost_out, grads
+
+    def replay(self):
+        """New rollout (next Philox key) + backward; afterwards cost_out / states / inputs / grads hold its results."""
+        p = self.pilco
+        p._rollouts += 1
+        word = (GOLDEN * p._rollouts) & MASK64
+        self.ctr.fill_(word - (1 << 64) if word >= (1 << 63) else word)  # the same 64 bits, as the int64 torch stores
+        self.graph.replay()
+        return self.cost_out[0], self.cost_out[1]
+
+    def deposit_grads(self):
+        for prm, k in zip(self.params, self.keys):
+            prm.grad = self.grads[k].view_as(prm)
 
 
 class MC_PILCO(torch.nn.Module):
@@ -120,22 +205,22 @@ class MC_PILCO(torch.nn.Module):
                 base = b.cpu()
             self._seed_base = int(base.item())
         self._rollouts += 1
-        return (self._seed_base + 0x9E3779B97F4A7C15 * self._rollouts) & ((1 << 64) - 1)
+        return (self._seed_base + GOLDEN * self._rollouts) & MASK64
 
-    def _initial_particles(self, mean, var, flg_uniform, up, low, flg_multi, count, offset, seed, noise):
+    def _initial_particles(self, mean, var, flg_uniform, up, low, flg_multi, count, offset, seed, noise, seed_dev=None):
         """Initial particle cloud (reference :635-657): Gaussian, uniform or multi-modal Gaussian."""
         dev = self.device
         as_dev = lambda v: torch.as_tensor(v, dtype=self.dtype, device=dev)  # noqa: E731
         if noise is not None and noise.get("x0") is not None:
             return as_dev(noise["x0"])
         if flg_uniform:
-            return ops.init_particles("uniform", as_dev(low).reshape(1, -1), as_dev(up).reshape(1, -1), count, seed, offset)
+            return ops.init_particles("uniform", as_dev(low).reshape(1, -1), as_dev(up).reshape(1, -1), count, seed, offset, seed_dev)
         mean, std = as_dev(mean), torch.sqrt(as_dev(var))
         if noise is not None and noise.get("eps0") is not None and not flg_multi:
             return mean.reshape(1, -1) + std.reshape(1, -1) * as_dev(noise["eps0"])
         if not flg_multi:
             mean, std = mean.reshape(1, -1), std.reshape(1, -1)
-        return ops.init_particles("gauss", mean, std, count, seed, offset)
+        return ops.init_particles("gauss", mean, std, count, seed, offset, seed_dev)
 
     def _meas_struct(self):
         return None
@@ -159,22 +244,32 @@ class MC_PILCO(torch.nn.Module):
                                      seed, _noise)
         params = [pol.log_lengthscales, pol.centers, pol.f_linear.weight] + ([pol.f_linear.bias] if pol.flg_bias else [])
         need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x0.requires_grad)
-        fused = self.cost_function.fused_spec(Ds, H, self._trial_index) if hasattr(self.cost_function, "fused_spec") else None
-        cst, ctraj = fused if fused is not None else (None, None)
-        if ctraj is not None:
-            ctraj = torch.as_tensor(ctraj, dtype=self.dtype, device=self.device)
-        nz = _noise or {}
-        plan = ops.RolloutPlan(ml.rollout_model_struct(Ds, Du), ml.fitted_gps(), pol.policy_struct(), pol.policy_tensors(), cost=cst,
-                               cost_traj=ctraj, meas=self._meas_struct(), M=count, H=H, p_dropout=p_dropout, seed=seed,
-                               particle_offset=offset, need_grad=need_grad, eps=nz.get("eps"), masks=nz.get("masks"),
-                               meas_eps=nz.get("meas_eps"), device=x0.device, M_global=int(num_particles))
-        states, inputs, cost, std = _ParticleRollout.apply(plan, x0, (rank, world, group, int(num_particles)), *params)
+        call = self._rollout_call(x0, count, offset, H, p_dropout, seed, _noise, int(num_particles))
+        fused = call.fused
+        states, inputs, cost, std = _ParticleRollout.apply(call, need_grad, x0, (rank, world, group, int(num_particles)), *params)
         if world > 1:
             states._mcp_shard = (rank, world, group, int(num_particles))  # Expected_cost's generic path merges across ranks with it
         if fused is not None:
             key = self._trial_index if getattr(self.cost_function, "flg_var_lengthscales", False) else None
             states._mcp_fused_cost = (self.cost_function, key, cost, std)
         return states, inputs
+
+    def _rollout_call(self, x0, count, offset, H, p_dropout, seed, noise, num_particles, seed_dev=None):
+        """Flatten the current model / policy / cost into the argument bundle of torch.ops.mcpilco.rollout_fwd / rollout_bwd."""
+        from .. import torch_ops as TO
+        Ds, Du = self.state_dim, self.input_dim
+        pol, ml = self.control_policy, self.model_learning
+        fused = self.cost_function.fused_spec(Ds, H, self._trial_index) if hasattr(self.cost_function, "fused_spec") else None
+        cst, ctraj = fused if fused is not None else (None, None)
+        if ctraj is not None:
+            ctraj = torch.as_tensor(ctraj, dtype=self.dtype, device=self.device)
+        nz = noise or {}
+        call = TO.RolloutCall(ml.rollout_model_struct(Ds, Du), ml.fitted_gps(), pol.policy_struct(), pol.policy_tensors(), cost=cst,
+                              cost_traj=ctraj, meas=self._meas_struct(), M=count, H=H, p_dropout=p_dropout, seed=seed, particle_offset=offset,
+                              eps=nz.get("eps"), masks=nz.get("masks"), meas_eps=nz.get("meas_eps"), M_global=int(num_particles),
+                              seed_dev=seed_dev)
+        call.fused = fused
+        return call
 
     def rollout(self, data_collection_index, T_rollout=None, particle_pred=False):
         """Open-loop model rollout along a recorded input trajectory (reference :347-373): one particle, mean prediction."""
@@ -211,14 +306,31 @@ class MC_PILCO(torch.nn.Module):
                     num_particles=num_particles, T_control=H)
         f_optim = eval(f_optimizer)
 
+        graphed = [None]
+
+        def graph_for(p_drop):
+            """The captured fwd + bwd rollout for the current policy tensors / dropout rate, or None (sharded run, user cost, switched off)."""
+            if not _GraphedRollout.eligible(self):
+                return None
+            if graphed[0] is None or graphed[0].signature != _GraphedRollout.signature_of(self, init, p_drop):
+                graphed[0] = _GraphedRollout(self, init, p_drop)
+            return graphed[0]
+
         def sample(p_drop):
-            """Rollout + cost, re-sampled up to 10 times while the cost is NaN; returns (states, inputs, cost, std, still_nan)."""
+            """Rollout + cost, re-sampled up to 10 times while the cost is NaN; returns (states, inputs, cost, std, still_nan, graph).
+            With a captured graph the rollout's backward pass has already run when this returns (gradients wait in the graph's
+            buffers); without one the caller runs cost.backward()."""
+            g = graph_for(p_drop)
             for _ in range(10):
-                states, inputs = self.apply_policy(p_dropout=p_drop, **init)
-                cost, std = self.cost_function(states, inputs, trial_index)
-                if not bool(torch.isnan(cost)):
-                    return states, inputs, cost, std, False
-            return states, inputs, cost, std, True
+                if g is not None:
+                    cost, std = g.replay()
+                    states, inputs = g.states, g.inputs
+                else:
+                    states, inputs = self.apply_policy(p_dropout=p_drop, **init)
+                    cost, std = self.cost_function(states, inputs, trial_index)
+                if not bool(torch.isnan(cost)):  # the one host synchronisation per step, as in the reference (MC_PILCO.py:497)
+                    return states, inputs, cost, std, False, g
+            return states, inputs, cost, std, True, g
 
         def fresh():
             z = lambda n: torch.zeros(n, device=self.device, dtype=self.dtype)  # noqa: E731
@@ -241,7 +353,7 @@ class MC_PILCO(torch.nn.Module):
         a = alpha_diff_cost
         while s["step"] < n_steps:
             optimizer.zero_grad()
-            states, inputs, cost, std, is_nan = sample(s["p_drop"])
+            states, inputs, cost, std, is_nan, g = sample(s["p_drop"])
             k = s["step"]
             s["cost"][k], s["std"][k] = cost.detach(), std.detach()
             with torch.no_grad():
@@ -250,7 +362,10 @@ class MC_PILCO(torch.nn.Module):
                 s["es2"] = a * (s["es2"] + (1 - a) * (dc - s["es1"][k]) ** 2)
                 cost_tm1 = s["cost"][k]
                 s["ratio"][k + 1] = a * s["ratio"][k] + (1 - a) * (s["es1"][k + 1] / s["es2"].sqrt())
-            cost.backward()
+            if g is not None:
+                g.deposit_grads()  # the captured backward pass already ran
+            else:
+                cost.backward()
             optimizer.step()
             if k % num_step_print == 0:
                 c = float(cost.detach())

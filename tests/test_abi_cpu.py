@@ -153,7 +153,7 @@ def test_argument_errors_are_reported_before_any_cuda_work(native):
     r.model.Ds, r.model.Du, r.model.E, r.model.D = 4, 1, 2, 7   # feature map would give 5
     assert L.mcpilco_rollout_fwd(C.byref(r), None) == E_ARG and b"does not match the feature map" in L.mcpilco_last_error()
     assert L.mcpilco_policy_forward(None, 3, 0, None, 0.0, None, 0, 0, None, None) == E_ARG
-    assert L.mcpilco_init_particles(2, None, None, 1, 4, 4, 0, 0, None, None) == E_ARG
+    assert L.mcpilco_init_particles(2, None, None, 1, 4, 4, 0, 0, None, None, None) == E_ARG
     assert L.mcpilco_ozaki_prepare(None, 4, 4, 8, None, None, None) == E_ARG
     # workspace queries are pure host arithmetic
     assert L.mcpilco_gp_precompute_workspace_bytes(300) > 2 * 320 * 320 * 8

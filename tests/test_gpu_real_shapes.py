@@ -227,3 +227,42 @@ def test_mixed_losses_vs_oracle_autograd(nh, mode):
     pol = obj.control_policy
     for a, b in ((pol.log_lengthscales, pol_o["log_ls"]), (pol.centers, pol_o["centers"]), (pol.f_linear.weight, pol_o["W"])):
         assert relmax(a.grad, b.grad.numpy()) < REL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the optimisation step with the rollout's forward + backward captured in a CUDA graph
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,numpy_init", [("c1", False), ("c3", True), ("c4", False)])
+def test_graphed_optimisation_step_is_bit_identical_to_the_eager_loop(nh, monkeypatch, capsys, name, numpy_init):
+    """reinforce_policy replays ONE captured graph per step (fresh Philox key through the device seed word) instead of enqueueing a
+    few hundred launches: same keys, same kernels, same Adam updates, so the cost / std histories and the final trajectories must be
+    bit-identical to the un-graphed loop (MCPILCO_NO_GRAPH=1).  numpy_init: initial distribution given as host arrays, like the
+    reference's scripts do (they must be staged outside the captured region)."""
+    import scenarios
+    import mcpilco_b200.policy_learning.MC_PILCO as MCP
+    sc = scenarios.scenario(name)
+    outs = {}
+    for mode in ("graph", "eager"):
+        if mode == "eager":
+            monkeypatch.setenv("MCPILCO_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("MCPILCO_NO_GRAPH", raising=False)
+        AB, obj, dev = _build_obj(sc)
+        T = AB.tensor_factory(dev)
+        conv = (lambda a: np.asarray(a)) if numpy_init else T
+        built = []
+        orig = MCP._GraphedRollout.__init__
+        monkeypatch.setattr(MCP._GraphedRollout, "__init__", lambda self, *a, **k: (built.append(1), orig(self, *a, **k))[1])
+        torch.manual_seed(0)
+        out = obj.reinforce_policy(T_control=sc["H"] * obj.T_sampling + 1e-9, num_particles=48, trial_index=0,
+                                   particles_initial_state_mean=conv(sc["x0_mean"]), particles_initial_state_var=conv(sc["x0_var"]),
+                                   flg_particles_init_uniform=False, particles_init_up_bound=None, particles_init_low_bound=None,
+                                   flg_particles_init_multi_gauss=False, opt_steps_list=[12], lr_list=[0.05],
+                                   f_optimizer="lambda p, lr : torch.optim.Adam(p, lr)", num_step_print=100, p_dropout_list=[0.1])
+        monkeypatch.setattr(MCP._GraphedRollout, "__init__", orig)
+        assert len(built) == (1 if mode == "graph" else 0)          # captured once, replayed 12 times
+        outs[mode] = out
+        assert np.isfinite(out[0]).all() and out[0].shape == (12,)
+    capsys.readouterr()
+    for a, b in zip(outs["graph"], outs["eager"]):
+        assert a.shape == b.shape and np.array_equal(a, b)
