@@ -28,6 +28,15 @@ class Expected_cost(torch.nn.modules.loss._Loss):
         """(McpCost, target trajectory tensor or None) when the CUDA rollout can evaluate this cost itself, else None."""
         return None
 
+    def fused_spec_cached(self, Ds, H, trial_index=None):
+        """fused_spec memoised on the object's tensor attributes (flattening reads them back to the host: not once per rollout)."""
+        key = (Ds, H, trial_index) + tuple((k, id(v), v._version, v.data_ptr()) for k, v in sorted(vars(self).items()) if isinstance(v, torch.Tensor))
+        hit = getattr(self, "_fused_memo", None)
+        if hit is None or hit[0] != key:
+            hit = (key, self.fused_spec(Ds, H, trial_index))
+            self._fused_memo = hit
+        return hit[1]
+
     def forward(self, states_sequence, inputs_sequence, trial_index=None):
         fused = getattr(states_sequence, "_mcp_fused_cost", None)
         if fused is not None and fused[0] is self and (fused[1] is None or fused[1] == trial_index):

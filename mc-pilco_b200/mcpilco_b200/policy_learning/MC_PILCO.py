@@ -116,6 +116,7 @@ class _GraphedRollout:
             pilco._next_seed()
             pilco._rollouts -= 1
         self.base = pilco._seed_base & MASK64
+        self.call = None
         # eager pass on the capture stream first: first-use initialisation of the native side (kernel attributes, the side streams and
         # scratch that are keyed by the launching stream) must not happen inside the captured region
         self.stream = torch.cuda.Stream(dev)
@@ -149,9 +150,11 @@ class _GraphedRollout:
         x0 = p._initial_particles(i["particles_initial_state_mean"], i["particles_initial_state_var"], i["flg_particles_init_uniform"],
                                   i["particles_init_up_bound"], i["particles_init_low_bound"], i["flg_particles_init_multi_gauss"], M, 0,
                                   self.base, None, seed_dev=self.ctr)
-        call = p._rollout_call(x0, M, 0, H, self.p_dropout, self.base, None, M, seed_dev=self.ctr)
-        states, inputs, cost_out, _, jac, pol_in = call.forward(x0, True)
-        grads = call.backward(x0, states, inputs, jac, pol_in, grad_cost=1.0)
+        if self.call is None:
+            # host-side flattening of model / policy / cost (reads a few device scalars): once, in the eager pass, never while capturing
+            self.call = p._rollout_call(x0, M, 0, H, self.p_dropout, self.base, None, M, seed_dev=self.ctr)
+        states, inputs, cost_out, _, jac, pol_in = self.call.forward(x0, True)
+        grads = self.call.backward(x0, states, inputs, jac, pol_in, grad_cost=1.0)
         return states, inputs, cost_out, grads
 
     def replay(self):
@@ -259,7 +262,9 @@ class MC_PILCO(torch.nn.Module):
         from .. import torch_ops as TO
         Ds, Du = self.state_dim, self.input_dim
         pol, ml = self.control_policy, self.model_learning
-        fused = self.cost_function.fused_spec(Ds, H, self._trial_index) if hasattr(self.cost_function, "fused_spec") else None
+        cf = self.cost_function
+        fused = (cf.fused_spec_cached(Ds, H, self._trial_index) if hasattr(cf, "fused_spec_cached") else
+                 cf.fused_spec(Ds, H, self._trial_index) if hasattr(cf, "fused_spec") else None)
         cst, ctraj = fused if fused is not None else (None, None)
         if ctraj is not None:
             ctraj = torch.as_tensor(ctraj, dtype=self.dtype, device=self.device)

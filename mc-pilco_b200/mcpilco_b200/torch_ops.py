@@ -184,9 +184,9 @@ def rollout_fwd(desc: torch.Tensor, gp_specs: torch.Tensor, gp_scalars: torch.Te
     plan = _plan(desc, gp_specs, gp_scalars, gp_tensors, log_ls, centers, W, bias, policy_traj, cost_traj, x0, eps, masks, meas_eps, seed_dev,
                  need_grad)
     states, inputs = plan.forward(x0)
-    none = x0.new_empty(0)
-    return (states, inputs, plan.cost_out if plan.cost_out is not None else none, plan.cost_stats if plan.cost_stats is not None else none,
-            plan.jac if plan.jac is not None else none, plan.pol_in if plan.pol_in is not None else none)
+    none = lambda: x0.new_empty(0)  # noqa: E731  (a fresh tensor per absent output: returns of a custom op must not alias each other)
+    return (states, inputs, plan.cost_out if plan.cost_out is not None else none(), plan.cost_stats if plan.cost_stats is not None else none(),
+            plan.jac if plan.jac is not None else none(), plan.pol_in if plan.pol_in is not None else none())
 
 
 @torch.library.custom_op("mcpilco::rollout_bwd", mutates_args=(), device_types="cuda")
@@ -203,8 +203,8 @@ def rollout_bwd(desc: torch.Tensor, gp_specs: torch.Tensor, gp_scalars: torch.Te
     plan.x0 = x0
     plan.r.x0 = x0.data_ptr()
     g = plan.backward(grad_cost=grad_cost, grad_states=grad_states, grad_inputs=grad_inputs, want_gx0=want_gx0)
-    none = x0.new_empty(0)
-    return g["log_ls"], g["centers"], g["W"], g["bias"] if g["bias"] is not None else none, g["x0"] if g["x0"] is not None else none
+    none = lambda: x0.new_empty(0)  # noqa: E731
+    return g["log_ls"], g["centers"], g["W"], g["bias"] if g["bias"] is not None else none(), g["x0"] if g["x0"] is not None else none()
 
 
 @rollout_fwd.register_fake
