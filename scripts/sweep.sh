@@ -3,7 +3,7 @@
 mkdir -p gpurun_out; : > gpurun_out/sweep.jsonl
 for cfg in "2048 8192" "4096 8192" "8192 4096" "8192 32768" "16384 8192"; do
   set -- $cfg
-  python bench.py --train-points $1 --particles-per-gpu $2 --steps 2 --warmup 2 --e2e-steps 1 --no-cpu-baseline 2>/dev/null >> gpurun_out/sweep.jsonl
+  python bench.py --train-points $1 --particles-per-gpu $2 --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-real-shapes 2>/dev/null >> gpurun_out/sweep.jsonl
 done
 python - <<'PY'
 import json
