@@ -412,24 +412,52 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
       for (int j = 0; j < Ds; j++) s_lnext[j] = 0.0;
       for (int i = 0; i < MCP_MAX_E; i++) s_lnv[i] = s_lmv[i] = s_lnp[i] = 0.0;
     }
+    // checkpoint of a step (x_t, policy input, u_t, Jacobian rows, upstream gradients): loaded one step AHEAD into registers, so the
+    // global round trip of step t-1 overlaps the serial stages of step t instead of opening every iteration
+    constexpr int JR = 8;  // E * D <= 256 Jacobian entries over >= 32 threads
+    double pre_x = 0.0, pre_px = 0.0, pre_gs = 0.0, pre_u = 0.0, pre_gi = 0.0, pre_J[JR];
+    auto prefetch = [&](int tt) {
+      const size_t row = (size_t)tt * M + m;
+      if (tid < Ds) {
+        pre_x = r.states[row * Ds + tid];
+        pre_px = polin[row * Ds + tid];
+        pre_gs = g.grad_states ? g.grad_states[row * Ds + tid] : 0.0;
+      }
+      if (tid < Du) {
+        pre_u = r.inputs[row * Du + tid];
+        pre_gi = g.grad_inputs ? g.grad_inputs[row * Du + tid] : 0.0;
+      }
+      if (tt < H - 1) {
+#pragma unroll
+        for (int k = 0; k < JR; k++) {
+          const int i = tid + k * (int)blockDim.x;
+          if (i < E * D) pre_J[k] = r.jac[row * E * D + i];
+        }
+      }
+    };
+    prefetch(H - 1);
     for (int t = H - 1; t >= 0; t--) {
-      // ---- stage 0: this step's checkpoint (x_t, policy input, u_t, Jacobian rows, upstream gradients) into shared memory with
-      //      one parallel, coalesced load instead of a chain of dependent scalar loads by the serial thread ----
+      // ---- stage 0: publish this step's (prefetched) checkpoint in shared memory, start fetching the previous step's ----
       {
-        const size_t row = (size_t)t * M + m;
         if (tid < Ds) {
-          s_x[tid] = r.states[row * Ds + tid];
-          s_px[tid] = polin[row * Ds + tid];
-          s_gs[tid] = g.grad_states ? g.grad_states[row * Ds + tid] : 0.0;
+          s_x[tid] = pre_x;
+          s_px[tid] = pre_px;
+          s_gs[tid] = pre_gs;
         }
         if (tid < Du) {
-          s_u[tid] = r.inputs[row * Du + tid];
-          s_gi[tid] = g.grad_inputs ? g.grad_inputs[row * Du + tid] : 0.0;
+          s_u[tid] = pre_u;
+          s_gi[tid] = pre_gi;
         }
-        if (t < H - 1)
-          for (int i = tid; i < E * D; i += blockDim.x) s_J[i] = r.jac[row * E * D + i];
+        if (t < H - 1) {
+#pragma unroll
+          for (int k = 0; k < JR; k++) {
+            const int i = tid + k * (int)blockDim.x;
+            if (i < E * D) s_J[i] = pre_J[k];
+          }
+        }
       }
       __syncthreads();
+      if (t > 0) prefetch(t - 1);
       const double* x = s_x;
       const double* px = s_px;
       const double* u = s_u;

@@ -109,23 +109,19 @@ __global__ void __launch_bounds__(SS_THREADS, 3) small_step_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < DT; j++) E1a[j] = E1v[j] = C1a[j] = C1v[j] = C2a0[j] = C2v0[j] = C2a1[j] = C2v1[j] = 0.0;
       const double* v = V + e * gp_stride + (size_t)m * ldk;
+      const double* kr = Ks + e * gp_stride + (size_t)m * ldk;  // the K* row of step t-1 (written by this block's pre(t-1) phase)
       for (int n = tid; n < N; n += SS_THREADS) {
         double y[DT];
         KFn<DT>::load(y, g.Xtr + (size_t)n * D, D);
-        const double a = g.alpha[n], vn = v[n];
-        double d2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < DT; j++) {
-          const double tt = fma(-y[j], s.inv_ls[j], xs[j]);
-          d2 = fma(tt, tt, d2);
-        }
-        const double ev = s.has_se ? s.lambda * exp(-d2) : 0.0;
-        double kv = ev, L2a = 0.0, L2b = 0.0;
+        const double a = g.alpha[n], vn = v[n], kv = kr[n];
+        // the kernel value is not evaluated again (cf. posterior_reduce_fast_kernel): polynomial factors from the particle-scaled
+        // weights, squared-exponential part e_n = k_n - poly_n
+        double poly = 0.0, L2a = 0.0, L2b = 0.0;
         if (NP >= 1) {
           double L1 = s.poly_w2[0][0][MCP_MAX_D];
 #pragma unroll
           for (int j = 0; j < DT; j++) L1 = fma(xw1[j], y[j], L1);
-          kv += L1;
+          poly = L1;
         }
         if (NP >= 2) {
           L2a = s.poly_w2[1][0][MCP_MAX_D];
@@ -135,8 +131,9 @@ __global__ void __launch_bounds__(SS_THREADS, 3) small_step_kernel(const __grid_
             L2a = fma(xw2a[j], y[j], L2a);
             L2b = fma(xw2b[j], y[j], L2b);
           }
-          kv = fma(L2a, L2b, kv);
+          poly = fma(L2a, L2b, poly);
         }
+        const double ev = kv - poly;
         mu = fma(a, kv, mu);
         q = fma(vn, kv, q);
         if (JAC) {
