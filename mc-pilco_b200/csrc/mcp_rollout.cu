@@ -16,6 +16,10 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
 bool small_path_ok(const McpRollout* r);
 size_t small_path_doubles(int M, int E, int Nmax);
 int rollout_fwd_small(const McpRollout* r, double* Xs, double* nv, double* scratch, size_t scratch_doubles, cudaStream_t st);
+// whole-horizon persistent cluster kernel for cart-pole-sized rollouts (mcp_persist.cu)
+bool persist_path_ok(const McpRollout* r);
+size_t persist_path_doubles(int E);
+int rollout_fwd_persist(const McpRollout* r, const double* nv0, double* scratch, size_t scratch_doubles, cudaStream_t st);
 struct McpGpDev;
 bool gp_posterior_batched_ok(const McpGp* gps, int E, bool jac);
 size_t gp_posterior_batched_doubles(int M, int E, int nmax);
@@ -777,8 +781,13 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
     init_nv_kernel<<<cdiv(M, 128), 128, 0, st>>>(r->meas, M, Ds, r->x0, w.nv);
     MCP_LAUNCH_CHECK();
   }
-  const bool small = small_path_ok(r) && w.scratch_doubles >= small_path_doubles(M, E, nmax);
-  if (small) {
+  // cart-pole-sized rollouts whose K^-1 fits a cluster's shared memory: ONE persistent kernel for the whole horizon
+  const bool persist = persist_path_ok(r) && w.scratch_doubles >= persist_path_doubles(E);
+  if (persist) {
+    if (int err = rollout_fwd_persist(r, w.nv, w.scratch, w.scratch_doubles, st)) return err;
+  }
+  const bool small = persist || (small_path_ok(r) && w.scratch_doubles >= small_path_doubles(M, E, nmax));
+  if (small && !persist) {
     if (int err = rollout_fwd_small(r, w.Xs, w.nv, w.scratch, w.scratch_doubles, st)) return err;
   }
   // small rollouts with wide gp inputs: all outputs of a step batched into three launches instead of E chains on side streams

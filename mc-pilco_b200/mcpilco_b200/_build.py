@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libmcpilco_b200.so")
-SOURCES = ["mcp_abi.cu", "mcp_dgemm.cu", "mcp_dgemm_tma.cu", "mcp_gp.cu", "mcp_nlml.cu", "mcp_sod.cu", "mcp_rollout.cu", "mcp_small.cu", "mcp_ozaki.cu", "mcp_ozaki_mma.cu"]
+SOURCES = ["mcp_abi.cu", "mcp_dgemm.cu", "mcp_dgemm_tma.cu", "mcp_gp.cu", "mcp_nlml.cu", "mcp_sod.cu", "mcp_rollout.cu", "mcp_small.cu", "mcp_persist.cu", "mcp_ozaki.cu", "mcp_ozaki_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -113,14 +113,17 @@ def _run_rollout(nh, sc, gps, fused_cost=True):
     return plan, states, inputs
 
 
-@pytest.fixture(params=["fused-small", "per-step"])
+@pytest.fixture(params=["persistent", "fused-small", "per-step"])
 def rollout_path(request, monkeypatch):
-    """Small rollouts take the fused two-launch-per-step kernels; MCPILCO_NO_SMALL_PATH=1 sends the same rollout through the per-step
-    kernels the large shapes use.  Both are held to the same golden vectors."""
+    """Cart-pole-sized rollouts (D <= 6) take the whole-horizon persistent cluster kernel, other small rollouts (and these with
+    MCPILCO_NO_PERSIST=1) the fused two-launch-per-step kernels; MCPILCO_NO_SMALL_PATH=1 sends the same rollout through the per-step
+    kernels the large shapes use.  All are held to the same golden vectors."""
+    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_PERSIST"):
+        monkeypatch.delenv(v, raising=False)
     if request.param == "per-step":
         monkeypatch.setenv("MCPILCO_NO_SMALL_PATH", "1")
-    else:
-        monkeypatch.delenv("MCPILCO_NO_SMALL_PATH", raising=False)
+    elif request.param == "fused-small":
+        monkeypatch.setenv("MCPILCO_NO_PERSIST", "1")
     return request.param
 
 
