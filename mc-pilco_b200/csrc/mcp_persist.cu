@@ -49,7 +49,7 @@ struct PkGeom {
   int Wt;   // W rounded up to the DMMA tile (8)
   int LD;   // row stride of the K* rows and of the K^-1 slice rows: = 4 (mod 16) doubles -> conflict-free DMMA fragment loads
   int WS;   // row stride of the per-warp channel-weight rows
-  size_t o_kinv, o_ks, o_v, o_wt, o_yf, o_al, o_feat, o_part, o_sum, o_own, o_spec, doubles;
+  size_t o_kinv, o_ks, o_v, o_vx, o_wt, o_yf, o_al, o_feat, o_part, o_sum, o_own, o_spec, o_bar, doubles;
 };
 __host__ __device__ inline PkGeom pk_geom(int Nmax, int E) {
   PkGeom g;
@@ -62,6 +62,7 @@ __host__ __device__ inline PkGeom pk_geom(int Nmax, int E) {
   g.o_kinv = o; o += (size_t)g.Wt * g.LD;
   g.o_ks = o;   o += (size_t)PK_P * g.LD;
   g.o_v = o;    o += (size_t)PK_P * g.Wt;
+  g.o_vx = o;   o += (size_t)(PK_WARPS / 2) * 64;                    // second K-halves of the matvec's last, partial round of tiles
   g.o_wt = o;   o += (size_t)PK_WARPS * 8 * g.WS;
   g.o_yf = o;   o += (size_t)E * 8 * g.WS;
   g.o_al = o;   o += (size_t)E * g.Wt;
@@ -70,6 +71,7 @@ __host__ __device__ inline PkGeom pk_geom(int Nmax, int E) {
   g.o_sum = o;  o += (size_t)PK_OWN * E * PK_NV;             // their sums, per output
   g.o_own = o;  o += (size_t)PK_OWN * 136;                   // owner-side particle state
   g.o_spec = o; o += (size_t)E * 40;                         // kernel hyper-parameters of each output (PkSpec)
+  g.o_bar = o;  o += 2;                                      // mbarrier of the K^-1 slice copies
   g.doubles = o;
   return g;
 }
@@ -96,6 +98,32 @@ __device__ __forceinline__ void pk_st_remote(const double* local, uint32_t rank,
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(pk_smem_u32(local)), "r"(rank));
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+// K^-1 slice rows arrive by bulk copies that complete on one mbarrier
+__device__ __forceinline__ void pk_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void pk_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pk_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void pk_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pk_smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 // barrier among the 64 threads that work on one owned particle (ids 1..PK_OWN; 0 is __syncthreads)
 __device__ __forceinline__ void pk_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -130,6 +158,7 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
   double* sKinv = pk_smem + G.o_kinv;   // [Wt][LD]  rows c0 .. c0 + Wt of K^-1 (= its columns)
   double* sKs = pk_smem + G.o_ks;       // [P][LD]   full K* rows of the batch for the current output
   double* sV = pk_smem + G.o_v;         // [P][Wt]
+  double* sVx = pk_smem + G.o_vx;       // [warps / 2][64]  upper-K halves of the tiles of the matvec's partial last round
   double* sWt = pk_smem + G.o_wt;       // [warps][8][WS]
   double* sYt = pk_smem + G.o_yf;       // [E][8][WS]  features of own columns, feature-major: y_0 .. y_5, 1, 0
   double* sAl = pk_smem + G.o_al;       // [E][Wt]
@@ -140,6 +169,8 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
   const int rank = (int)pk_rank(), c0 = rank * G.W;
   const int nclusters = gridDim.x / PK_CL, cid = (int)pk_cluster_id();
+  const int items = PK_MT * (G.Wt / 8), items_full = items / PK_WARPS * PK_WARPS;
+  const bool split_tail = items > items_full && 2 * (items - items_full) <= PK_WARPS;
   const bool drop = dropout_active(pol, nz);
   const double keep_scale = drop ? 1.0 / (1.0 - nz.p_dropout) : 1.0;
   const uint64_t seed = noise_seed(nz);
@@ -173,26 +204,34 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
     for (int j = 0; j < 8; j++) sYt[((size_t)e * 8 + j) * G.WS + c] = (ok && j < D) ? g.Xtr[(size_t)cg * D + j] : (ok && j == 6 ? 1.0 : 0.0);
     sAl[i] = ok ? g.alpha[cg] : 0.0;
   }
-  // K^-1 slice of output e -> sKinv (asynchronous; rows / columns past N_e are zero-filled)
-  auto load_slice = [&](int e) {
-    const McpGpDev& g = gps[e];
-    const int Ne = g.N, ldg = g.ld;
-    const double* Kg = g.Kinv;
-    for (int rr = warp; rr < G.Wt; rr += PK_WARPS) {   // warps over slice rows, lanes over 16-byte chunks: no index division
-      const int cg = c0 + rr;
-      const bool row_ok = rr < G.W && cg < Ne;
-      const double* src = Kg + (size_t)(row_ok ? cg : 0) * ldg;
-      double* dst = sKinv + (size_t)rr * G.LD;
-      for (int k = 2 * lane; k < G.Kc; k += 64) {
-        const int left = row_ok ? Ne - k : 0;
-        const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-        cp_async16(dst + k, src + (bytes ? k : 0), bytes);
+  // K^-1 slice of output e -> sKinv: one bulk copy per slice row, all completing on one mbarrier.  Every output has the same N
+  // (persist_path_ok), so the zero padding (columns past N, rows past the slice) is written once here and never overwritten.
+  const uint32_t bar = pk_smem_u32(pk_smem + G.o_bar);
+  const int Nall = gps[0].N, Ncopy = Nall & ~1;   // bulk copies move multiples of 16 bytes; an odd last element goes by hand
+  if (tid == 0) pk_mbar_init(bar, 1);
+  for (int rr = warp; rr < G.Wt; rr += PK_WARPS) {
+    const bool row_ok = rr < G.W && c0 + rr < Nall;
+    for (int k = (row_ok ? Nall : 0) + lane; k < G.LD; k += 32) sKinv[(size_t)rr * G.LD + k] = 0.0;
+  }
+  __syncthreads();
+  int rows_ok = G.W < Nall - c0 ? G.W : Nall - c0;
+  rows_ok = rows_ok < 0 ? 0 : rows_ok;
+  uint32_t slices_issued = 0;
+  auto load_slice = [&](int e) {   // called by all threads, issued by warp 0
+    slices_issued++;
+    if (warp == 0) {
+      const McpGpDev& g = gps[e];
+      if (lane == 0) pk_mbar_expect_tx(bar, (uint32_t)rows_ok * (uint32_t)Ncopy * 8u);
+      __syncwarp();
+      for (int rr = lane; rr < rows_ok; rr += 32) {
+        const double* src = g.Kinv + (size_t)(c0 + rr) * g.ld;
+        double* dst = sKinv + (size_t)rr * G.LD;
+        if (Ncopy > 0) pk_bulk_g2s(dst, src, (uint32_t)Ncopy * 8u, bar);
+        if (Ncopy != Nall) dst[Nall - 1] = src[Nall - 1];
       }
     }
-    cp_async_commit();
   };
   load_slice(0);
-  int slice_of = 0;
 
   for (int batch = cid; batch * PK_P < M; batch += nclusters) {
     const int base = batch * PK_P, cnt = min(PK_P, M - base);
@@ -321,13 +360,11 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
               o.pin[ltid] = ms.enabled ? r.pol_in[(size_t)m * Ds + ltid] : o.x[ltid];
             }
             if (ms.enabled && ltid < ms.n_pos) o.nv[ltid] = nv0[(size_t)m * ms.n_pos + ltid];
+            if (ltid < pol.Dp) o.il[ltid] = exp(-pol.log_ls[ltid]);
           }
           pk_pair_sync(1 + lp);
           // ---- policy (64 threads over the basis functions), cf. policy_fwd_block_kernel ----
-          if (ltid < pol.Dp) {
-            o.il[ltid] = exp(-pol.log_ls[ltid]);
-            o.z[ltid] = policy_feature(pol, o.pin, t, ltid);
-          }
+          if (ltid < pol.Dp) o.z[ltid] = policy_feature(pol, o.pin, t, ltid);
           pk_pair_sync(1 + lp);
           {
             double a[PK_MAX_DU];
@@ -346,23 +383,32 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
                   for (int i = 0; i < 4; i++) keep[i] = (double)pq.v[i] * (1.0 / 4294967296.0) >= nz.p_dropout;
                 }
               }
+              // clamped indices instead of branches: all the (L2-latency) loads of the four basis functions issue together
+              const double* cb[4];
+              double d[4], wv[4][PK_MAX_DU];
 #pragma unroll
               for (int i = 0; i < 4; i++) {
-                const int b = b0 + i;
-                if (b < pol.nb) {
-                  const double* c = pol.centers + (size_t)b * pol.Dp;
-                  double d = 0.0;
-#pragma unroll 8
-                  for (int j = 0; j < pol.Dp; j++) {
-                    const double rr = (o.z[j] - c[j]) * o.il[j];
-                    d = fma(rr, rr, d);
-                  }
-                  double h = exp(-d);
-                  if (drop) h = keep[i] ? h * keep_scale : 0.0;
+                const int b = min(b0 + i, pol.nb - 1);
+                cb[i] = pol.centers + (size_t)b * pol.Dp;
+                d[i] = 0.0;
 #pragma unroll
-                  for (int k = 0; k < PK_MAX_DU; k++)
-                    if (k < pol.Du) a[k] = fma(pol.W[(size_t)k * pol.nb + b], h, a[k]);
+                for (int k = 0; k < PK_MAX_DU; k++) wv[i][k] = pol.W[(size_t)min(k, pol.Du - 1) * pol.nb + b];
+              }
+#pragma unroll 4
+              for (int j = 0; j < pol.Dp; j++) {
+                const double zj = o.z[j], ilj = o.il[j];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  const double rr = (zj - cb[i][j]) * ilj;
+                  d[i] = fma(rr, rr, d[i]);
                 }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                double h = (b0 + i < pol.nb && keep[i]) ? exp(-d[i]) * keep_scale : 0.0;
+#pragma unroll
+                for (int k = 0; k < PK_MAX_DU; k++)
+                  if (k < pol.Du) a[k] = fma(wv[i][k], h, a[k]);
               }
             }
 #pragma unroll
@@ -449,33 +495,41 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
             }
           }
         }
-        cp_async_wait<0>();
-        pk_cluster_sync();  // K* rows complete in every CTA (also makes this CTA's K^-1 slice visible to all its threads)
+        pk_cluster_sync();  // K* rows complete in every CTA
+        pk_mbar_wait(bar, (slices_issued - 1) & 1);   // this output's K^-1 slice has landed (a no-op once E = 1 has its only slice)
 
         // =========================================================== V[:, own columns] = K* K^-1[:, own columns] on FP64 DMMA
         {
-          const int ctiles = G.Wt / 8, items = PK_MT * ctiles;
-          for (int it = warp; it < items; it += PK_WARPS) {
+          // tile (mt, ct) of V: full rounds of eight tiles, one per warp; a last partial round of <= 4 tiles is split in two K halves
+          // over warp pairs (the upper halves go to sVx and are added by the consumer) so that no warp idles through a whole round
+          auto tile = [&](int it, int k_lo, int k_hi, double* upper) {   // upper: the 8 x 8 block of sVx for an upper K half, else nullptr
             const int mt = it % PK_MT, ct = it / PK_MT, row = mt * 8 + gq;
             const double* A = sKs + (size_t)min(row, PK_P - 1) * G.LD + q;
             const double* B = sKinv + (size_t)(ct * 8 + gq) * G.LD + q;
             double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-            for (int k = 0; k < G.Kc; k += 8) {   // Kc is a multiple of 16; two independent accumulation chains
+            for (int k = k_lo; k < k_hi; k += 8) {   // two independent accumulation chains
               dmma884(a0, a1, A[k], B[k]);
               dmma884(b0, b1, A[k + 4], B[k + 4]);
             }
-            if (row < PK_P) {
-              double* out = sV + (size_t)row * G.Wt + ct * 8 + 2 * q;
-              out[0] = a0 + b0;
-              out[1] = a1 + b1;
+            if (upper != nullptr || row < PK_P) {
+              double* o2 = upper != nullptr ? upper + gq * 8 + 2 * q : sV + (size_t)row * G.Wt + ct * 8 + 2 * q;
+              o2[0] = a0 + b0;
+              o2[1] = a1 + b1;
             }
+          };
+          for (int it = warp; it < items_full; it += PK_WARPS) tile(it, 0, G.Kc, nullptr);
+          if (split_tail) {
+            const int it = items_full + (warp >> 1);
+            if (it < items) {
+              if (warp & 1) tile(it, G.Kc / 2, G.Kc, sVx + (size_t)(warp >> 1) * 64);
+              else tile(it, 0, G.Kc / 2, nullptr);
+            }
+          } else if (items_full + warp < items) {
+            tile(items_full + warp, 0, G.Kc, nullptr);
           }
         }
         __syncthreads();
-        if (E > 1) {  // the slice buffer is free: stream the next output's slice in behind the reduce
-          slice_of = (e + 1) % E;
-          load_slice(slice_of);
-        }
+        if (E > 1) load_slice((e + 1) % E);  // the slice buffer is free: stream the next output's slice in behind the reduce
 
         // =========================================================== own columns' share of the factored posterior sums
         for (int ml = warp; ml < cnt; ml += PK_WARPS) {
@@ -494,7 +548,11 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
 #pragma unroll
             for (int j = 0; j < DT; j++) y[j] = sYt[((size_t)e * 8 + j) * G.WS + c];
             const double a = sAl[e * G.Wt + c];
-            const double vn = sV[(size_t)ml * G.Wt + c];
+            double vn = sV[(size_t)ml * G.Wt + c];
+            if (split_tail) {
+              const int it = (c >> 3) * PK_MT + (ml >> 3);
+              if (it >= items_full) vn += sVx[(size_t)(it - items_full) * 64 + (ml & 7) * 8 + (c & 7)];
+            }
             const double kv = (c < G.W && c0 + c < G.Kc) ? sKs[(size_t)ml * G.LD + c0 + c] : 0.0;
             double poly = 0.0, L2a = 0.0, L2b = 0.0;
             if (NP >= 1) {
@@ -552,7 +610,7 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
     }
     __syncthreads();
   }
-  cp_async_wait<0>();
+  pk_mbar_wait(bar, (slices_issued - 1) & 1);  // no bulk copy in flight at exit
   pk_cluster_sync();  // no CTA leaves while a peer may still store into its shared memory
 }
 
@@ -575,6 +633,7 @@ bool persist_path_ok(const McpRollout* r) {
     if (np >= 0 && s.n_poly != np) return false;
     np = s.n_poly;
     if (r->gps[e].ld_kinv % 2 != 0 || ((uintptr_t)r->gps[e].Kinv % 16) != 0) return false;
+    if (r->gps[e].N != r->gps[0].N) return false;  // one zero padding of the slice buffer serves every output
     nmax = r->gps[e].N > nmax ? r->gps[e].N : nmax;
   }
   return pk_geom(nmax, r->model.E).doubles * sizeof(double) <= 227 * 1024;
