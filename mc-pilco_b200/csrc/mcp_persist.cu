@@ -450,49 +450,41 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
 
       for (int e = 0; e < E; e++) {
         // =========================================================== K* entries of own columns for all particles -> every CTA's sKs
-        // thread <-> (column c = tid % 64, row group tid / 64): the column's scaled inputs stay in registers over the particle loop
         const PkSpec& sp = sSpec[e];
         const int Ne = sp.N;
+        // (particle, own column) pairs spread over all threads, a warp's lanes on consecutive columns; columns past N keep the zero
+        // the batch-start clear gave them
         {
-          const int c = tid & 63, rg = tid >> 6, cg = c0 + c;
-          if (c < G.W && cg < G.Kc) {
-            const bool col_ok = cg < Ne;
-            double y[DT], ys[DT];
+          const int Wv = max(0, min(G.W, Ne - c0)), nitems = Wv * cnt;
+          for (int i = tid; i < nitems; i += PK_THREADS) {
+            const int ml = i / Wv, c = i - ml * Wv;
+            const double* x = sFeat + ml * 8;
+            double y[DT], d2 = 0.0;
 #pragma unroll
             for (int j = 0; j < DT; j++) {
               y[j] = sYt[((size_t)e * 8 + j) * G.WS + c];
-              ys[j] = y[j] * sp.ils[j];
+              const double tt = (x[j] - y[j]) * sp.ils[j];
+              d2 = fma(tt, tt, d2);
             }
-            for (int ml = rg; ml < cnt; ml += PK_THREADS / 64) {
-              double kv = 0.0;
-              if (col_ok) {
-                const double* x = sFeat + ml * 8;
-                double d2 = 0.0;
+            double kv = sp.has_se ? sp.lambda * exp(-d2) : 0.0;
+            if (NP >= 1) {
+              double L1 = sp.o1;
 #pragma unroll
-                for (int j = 0; j < DT; j++) {
-                  const double tt = (x[j] * sp.ils[j]) - ys[j];
-                  d2 = fma(tt, tt, d2);
-                }
-                kv = sp.has_se ? sp.lambda * exp(-d2) : 0.0;
-                if (NP >= 1) {
-                  double L1 = sp.o1;
+              for (int j = 0; j < DT; j++) L1 = fma(sp.w1[j] * x[j], y[j], L1);
+              kv += L1;
+            }
+            if (NP >= 2) {
+              double La = sp.o2a, Lb = sp.o2b;
 #pragma unroll
-                  for (int j = 0; j < DT; j++) L1 = fma(sp.w1[j] * x[j], y[j], L1);
-                  kv += L1;
-                }
-                if (NP >= 2) {
-                  double La = sp.o2a, Lb = sp.o2b;
-#pragma unroll
-                  for (int j = 0; j < DT; j++) {
-                    La = fma(sp.w2a[j] * x[j], y[j], La);
-                    Lb = fma(sp.w2b[j] * x[j], y[j], Lb);
-                  }
-                  kv = fma(La, Lb, kv);
-                }
+              for (int j = 0; j < DT; j++) {
+                La = fma(sp.w2a[j] * x[j], y[j], La);
+                Lb = fma(sp.w2b[j] * x[j], y[j], Lb);
               }
-#pragma unroll
-              for (int dst = 0; dst < PK_CL; dst++) pk_st_remote(&sKs[(size_t)ml * G.LD + cg], (uint32_t)dst, kv);
+              kv = fma(La, Lb, kv);
             }
+            const double* dstp = &sKs[(size_t)ml * G.LD + c0 + c];
+#pragma unroll
+            for (int dst = 0; dst < PK_CL; dst++) pk_st_remote(dstp, (uint32_t)dst, kv);
           }
         }
         pk_cluster_sync();  // K* rows complete in every CTA
@@ -585,10 +577,15 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
           __syncwarp();
           // tile[channel][feature] = sum_c weight[channel][c] feature[c][.]  with features [y_0..y_5, 1, k_c]
           // (feature 7 is read from the K* row itself: columns past this CTA's slice carry zero weight, the row padding is zero)
-          double t0 = 0.0, t1 = 0.0;
+          double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
           const double* bbase = (gq == 7) ? sKs + (size_t)ml * G.LD + c0 + q : sYt + ((size_t)e * 8 + gq) * G.WS + q;
           const double* abase = wt + gq * G.WS + q;
-          for (int k = 0; k < G.Wt; k += 4) dmma884(t0, t1, abase[k], bbase[k]);
+          for (int k = 0; k < G.Wt; k += 8) {   // Wt is a multiple of 8: two accumulation chains
+            dmma884(t0, t1, abase[k], bbase[k]);
+            dmma884(u0, u1, abase[k + 4], bbase[k + 4]);
+          }
+          t0 += u0;
+          t1 += u1;
           __syncwarp();
           // lane (gq, q) holds tile[gq][2q], tile[gq][2q+1]: send to the particle's owner
           const int owner = ml % PK_CL, lp = ml / PK_CL;
@@ -636,7 +633,13 @@ bool persist_path_ok(const McpRollout* r) {
     if (r->gps[e].N != r->gps[0].N) return false;  // one zero padding of the slice buffer serves every output
     nmax = r->gps[e].N > nmax ? r->gps[e].N : nmax;
   }
-  return pk_geom(nmax, r->model.E).doubles * sizeof(double) <= 227 * 1024;
+  if (pk_geom(nmax, r->model.E).doubles * sizeof(double) > 227 * 1024) return false;
+  // Eligible.  Measured on B200 against the fused two-launch-per-step path (profiles/r02_real_shape_paths.txt): with Volterra terms
+  // in the kernel (C1) this path is faster at every N that fits; with SE-only outputs (C2, C3) it is faster up to N ~ 250 and a few
+  // per cent slower at N = 300, where the per-step DMMA work outgrows the launch latency it saves.  MCPILCO_PERSIST=1 forces it.
+  const char* force = getenv("MCPILCO_PERSIST");
+  if (force != nullptr && force[0] == '1') return true;
+  return np >= 1 || nmax <= 240;
 }
 
 size_t persist_path_doubles(int E) { return (sizeof(McpGpDev) * (size_t)E + 7) / 8 + 64; }

@@ -78,6 +78,9 @@ def time_cpu(sc, threads, reps=2):
 def main():
     rs = np.random.RandomState(0)
     shapes = [("c1", 300, 400, 60, 200), ("c2", 300, 400, 60, 200), ("c3", 300, 400, 90, 200), ("c4", 400, 200, 200, 400), ("c1", 60, 400, 60, 200)]
+    nsel = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--N=")]
+    if nsel:
+        shapes = [s for s in shapes if s[1] in nsel]
     only = [a.split("=")[1] for a in sys.argv if a.startswith("--only=")]
     reps = int(([a.split("=")[1] for a in sys.argv if a.startswith("--reps=")] or ["20"])[0])
     for name, N, M, H, nb in shapes:

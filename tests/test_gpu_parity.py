@@ -118,9 +118,11 @@ def rollout_path(request, monkeypatch):
     """Cart-pole-sized rollouts (D <= 6) take the whole-horizon persistent cluster kernel, other small rollouts (and these with
     MCPILCO_NO_PERSIST=1) the fused two-launch-per-step kernels; MCPILCO_NO_SMALL_PATH=1 sends the same rollout through the per-step
     kernels the large shapes use.  All are held to the same golden vectors."""
-    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_PERSIST"):
+    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_PERSIST", "MCPILCO_PERSIST"):
         monkeypatch.delenv(v, raising=False)
-    if request.param == "per-step":
+    if request.param == "persistent":
+        monkeypatch.setenv("MCPILCO_PERSIST", "1")   # wherever eligible, not only where the default heuristic picks it
+    elif request.param == "per-step":
         monkeypatch.setenv("MCPILCO_NO_SMALL_PATH", "1")
     elif request.param == "fused-small":
         monkeypatch.setenv("MCPILCO_NO_PERSIST", "1")

@@ -42,7 +42,7 @@ def oracle_of(key, sc):
     return _oracle_cache[key]
 
 
-PATHS = {"persistent": {}, "fused-small": {"MCPILCO_NO_PERSIST": "1"}, "per-step": {"MCPILCO_NO_SMALL_PATH": "1"},
+PATHS = {"persistent": {"MCPILCO_PERSIST": "1"}, "fused-small": {"MCPILCO_NO_PERSIST": "1"}, "per-step": {"MCPILCO_NO_SMALL_PATH": "1"},
          "per-output-chains": {"MCPILCO_NO_SMALL_PATH": "1", "MCPILCO_NO_BATCHED_STEP": "1"}, "no-pdl": {"MCPILCO_NO_PERSIST": "1", "MCPILCO_NO_PDL": "1"}}
 CASES = [("c1", "persistent"), ("c1", "fused-small"), ("c1", "per-step"), ("c1", "no-pdl"), ("c2", "persistent"), ("c2", "fused-small"),
          ("c2", "per-step"), ("c3", "persistent"), ("c3", "fused-small"), ("c3", "per-step"), ("c4", "per-step"), ("c4", "per-output-chains"),
@@ -70,7 +70,7 @@ def check(nh, sc, ref, tag):
 @pytest.mark.parametrize("key,path", CASES)
 def test_real_shape_rollout_vs_oracle(nh, monkeypatch, key, path):
     from mcpilco_b200 import workloads as W
-    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_BATCHED_STEP", "MCPILCO_NO_PDL", "MCPILCO_NO_PERSIST"):
+    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_BATCHED_STEP", "MCPILCO_NO_PDL", "MCPILCO_NO_PERSIST", "MCPILCO_PERSIST"):
         monkeypatch.delenv(v, raising=False)
     for k, v in PATHS[path].items():
         monkeypatch.setenv(k, v)
