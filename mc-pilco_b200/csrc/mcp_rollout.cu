@@ -378,28 +378,44 @@ __global__ void cost_final_kernel(int M, int H, const double* __restrict__ stats
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: reverse sweep over the horizon, one CTA per particle (grid-strided), thread <-> basis function
+// backward: reverse sweep over the horizon, one CTA per particle (grid-strided).
+// The adjoint recursion lambda_{t+1} -> lambda_t is one serial chain per particle, so the kernel is organised around the length of
+// that chain and nothing else:
+//   * the first ceil(nb / 32) warps own one policy basis function per thread; one extra warp (the "chain warp") carries the adjoints,
+//     lane j holding component j;
+//   * everything that does not depend on the incoming adjoint is computed AHEAD of the chain by the basis threads while the chain
+//     warp works: the checkpoint of step t-5 streams global -> shared (cp.async, ring of 8 slots), the policy features, the cost
+//     gradient and the sines / cosines of step t-2 are derived from the ring (ring of 4), and the basis activations h_b (exp, dropout
+//     draw) of step t-1 sit in a register when the chain reaches that step;
+//   * per step two block barriers remain: [basis part of the policy adjoint] Z [chain warp: cross-warp sums, policy-input adjoint,
+//     measurement model, model step t-1 -> adjoint of u_{t-1}] Y.
+// Reference: the autograd graph of apply_policy (policy_learning/MC_PILCO.py:615-674, :808-906) walked by cost.backward() (:522).
 // ------------------------------------------------------------------------------------------------
-template <int DPT, int DUT>
-__global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant__ McpRollout r, const __grid_constant__ McpRolloutGrad g,
+constexpr int BW_RING = 8, BW_AUX = 4, BW_LAG = 5;
+
+template <int DPT, int DUT, int NT, int NCTA>
+__global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_constant__ McpRollout r, const __grid_constant__ McpRolloutGrad g,
                                                            double* __restrict__ partials, double* __restrict__ g_x0) {
+  extern __shared__ double bw_ring[];  // [BW_RING][x | policy input | grad_states | u | grad_inputs | Jacobian rows]
   const McpModel& mdl = r.model;
   const McpPolicy& pol = r.policy;
   const McpMeas& ms = r.meas;
   const int M = r.M, H = r.H, Ds = mdl.Ds, Du = mdl.Du, E = mdl.E, D = mdl.D, nb = pol.nb, Dp = pol.Dp;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbw = (nb + 31) >> 5, nbt = nbw * 32;  // basis warps / threads; warp nbw is the chain warp
+  const bool chain = warp == nbw;
   const int b = tid;
   const bool has_b = b < nb;
+  const int o_px = Ds, o_gs = 2 * Ds, o_u = 3 * Ds, o_gi = 3 * Ds + Du, o_J = 3 * Ds + 2 * Du, slot_n = o_J + E * D;
 
-  __shared__ double s_il[MCP_MAX_DP], s_z[MCP_MAX_DP], s_lz[MCP_MAX_DP], s_glz[MCP_MAX_DP];
-  __shared__ double s_lam[MCP_MAX_DS], s_lnext[MCP_MAX_DS], s_la[MCP_MAX_DU], s_gbias[MCP_MAX_DU];
-  __shared__ double s_lnv[MCP_MAX_E], s_lmv[MCP_MAX_E], s_lnp[MCP_MAX_E];
+  __shared__ double s_il[MCP_MAX_DP];
+  __shared__ double s_z[BW_AUX][MCP_MAX_DP], s_lam0[BW_AUX][MCP_MAX_DS];
+  __shared__ double s_msin[BW_AUX][MCP_MAX_DS], s_mcos[BW_AUX][MCP_MAX_DS], s_psin[BW_AUX][MCP_MAX_DS], s_pcos[BW_AUX][MCP_MAX_DS];
+  __shared__ double s_lnext[MCP_MAX_DS], s_lx[MCP_MAX_D], s_la[MCP_MAX_DU], s_lz[MCP_MAX_DP];
   __shared__ double s_red[16][MCP_MAX_DP];
-  __shared__ double s_x[MCP_MAX_DS], s_px[MCP_MAX_DS], s_gs[MCP_MAX_DS], s_u[MCP_MAX_DU], s_gi[MCP_MAX_DU], s_J[MCP_MAX_E * MCP_MAX_D];
   __shared__ int s_active;
 
-  if (tid < Dp) { s_il[tid] = exp(-pol.log_ls[tid]); s_glz[tid] = 0.0; }
-  if (tid < MCP_MAX_DU) s_gbias[tid] = 0.0;
+  if (tid < Dp) s_il[tid] = exp(-pol.log_ls[tid]);
   double cb[DPT], gc[DPT], wb[DUT], gw[DUT];
 #pragma unroll
   for (int j = 0; j < DPT; j++) { cb[j] = (has_b && j < Dp) ? pol.centers[(size_t)b * Dp + j] : 0.0; gc[j] = 0.0; }
@@ -409,207 +425,248 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
   const double keep_scale = drop ? 1.0 / (1.0 - r.noise.p_dropout) : 1.0;
   const double cost_w = (r.cost.kind != 0) ? g.grad_cost / (double)M : 0.0;  // adds to grad_states / grad_inputs when both are given
   const double* polin = (ms.enabled && r.pol_in) ? r.pol_in : r.states;
+  // chain-warp registers: lane j carries component j
+  double glz = 0.0, gbias = 0.0;  // log-lengthscale gradient (first half, see below), bias gradient
   __syncthreads();
 
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
-    if (tid == 0) {
-      for (int j = 0; j < Ds; j++) s_lnext[j] = 0.0;
-      for (int i = 0; i < MCP_MAX_E; i++) s_lnv[i] = s_lmv[i] = s_lnp[i] = 0.0;
-    }
-    // checkpoint of a step (x_t, policy input, u_t, Jacobian rows, upstream gradients): loaded one step AHEAD into registers, so the
-    // global round trip of step t-1 overlaps the serial stages of step t instead of opening every iteration
-    constexpr int JR = 8;  // E * D <= 256 Jacobian entries over >= 32 threads
-    double pre_x = 0.0, pre_px = 0.0, pre_gs = 0.0, pre_u = 0.0, pre_gi = 0.0, pre_J[JR];
-    auto prefetch = [&](int tt) {
-      const size_t row = (size_t)tt * M + m;
-      if (tid < Ds) {
-        pre_x = r.states[row * Ds + tid];
-        pre_px = polin[row * Ds + tid];
-        pre_gs = g.grad_states ? g.grad_states[row * Ds + tid] : 0.0;
+    // ---- helpers --------------------------------------------------------------------------------------------------------------
+    // checkpoint of step tt: global -> ring slot, asynchronously (basis threads; one commit group per call, empty past the start)
+    auto issue = [&](int tt) {
+      if (tt >= 0) {
+        double* slot = bw_ring + (size_t)(tt & (BW_RING - 1)) * slot_n;
+        const size_t row = (size_t)tt * M + m;
+        for (int i = tid; i < slot_n; i += nbt) {
+          const double* src = nullptr;
+          if (i < o_px) src = r.states + row * Ds + i;
+          else if (i < o_gs) src = polin + row * Ds + (i - o_px);
+          else if (i < o_u) src = g.grad_states ? g.grad_states + row * Ds + (i - o_gs) : nullptr;
+          else if (i < o_gi) src = r.inputs + row * Du + (i - o_u);
+          else if (i < o_J) src = g.grad_inputs ? g.grad_inputs + row * Du + (i - o_gi) : nullptr;
+          else src = (tt < H - 1) ? r.jac + row * E * D + (i - o_J) : nullptr;
+          cp_async8(slot + i, src ? src : r.states, src ? 8 : 0);
+        }
       }
-      if (tid < Du) {
-        pre_u = r.inputs[row * Du + tid];
-        pre_gi = g.grad_inputs ? g.grad_inputs[row * Du + tid] : 0.0;
-      }
-      if (tt < H - 1) {
-#pragma unroll
-        for (int k = 0; k < JR; k++) {
-          const int i = tid + k * (int)blockDim.x;
-          if (i < E * D) pre_J[k] = r.jac[row * E * D + i];
+      cp_async_commit();
+    };
+    // adjoint-independent quantities of step tt from its ring slot (basis threads, one role each)
+    auto aux = [&](int tt) {
+      if (tt < 0) return;
+      const double* slot = bw_ring + (size_t)(tt & (BW_RING - 1)) * slot_n;
+      const int a = tt & (BW_AUX - 1);
+      const int n_ma = mdl.use_trig ? mdl.n_a : 0, n_pa = (pol.kind == 1) ? pol.n_a : 0;
+      const int nroles = Dp + 1 + n_ma + n_pa;
+      for (int role = tid; role < nroles; role += nbt) {
+        if (role < Dp) {
+          s_z[a][role] = policy_feature(pol, slot + o_px, tt, role);
+        } else if (role == Dp) {  // adjoint of x_tt from the caller's gradient and the fused cost
+          for (int j = 0; j < Ds; j++) s_lam0[a][j] = slot[o_gs + j];
+          if (cost_w != 0.0) cost_grad_add(r.cost, slot, tt, Ds, cost_w, s_lam0[a]);
+        } else if (role < Dp + 1 + n_ma) {
+          const int i = role - Dp - 1;
+          double sn, cs;
+          sincos(slot[mdl.a_idx[i]], &sn, &cs);
+          s_msin[a][i] = sn;
+          s_mcos[a][i] = cs;
+        } else {
+          const int i = role - Dp - 1 - n_ma;
+          double sn, cs;
+          sincos(slot[o_px + pol.a_idx[i]], &sn, &cs);
+          s_psin[a][i] = sn;
+          s_pcos[a][i] = cs;
         }
       }
     };
-    prefetch(H - 1);
+    // activation of this thread's basis function at step tt (needs aux(tt))
+    auto activation = [&](int tt) {
+      double h = 0.0;
+      if (has_b && tt >= 0) {
+        const double* z = s_z[tt & (BW_AUX - 1)];
+        double d = 0.0;
+#pragma unroll
+        for (int j = 0; j < DPT; j++)
+          if (j < Dp) { double q = (z[j] - cb[j]) * s_il[j]; d = fma(q, q, d); }
+        h = exp(-d);
+        if (drop) h = keep_unit(r.noise, M, nb, tt, tt, m, b) ? h * keep_scale : 0.0;
+      }
+      return h;
+    };
+    // chain warp, stage A of step tt: adjoint of x_tt from the cost and from the model step tt -> tt+1 (lane j: component j, returned);
+    // adjoint of u_tt -> s_la, s_active
+    auto chain_A = [&](int tt) {
+      const double* slot = bw_ring + (size_t)(tt & (BW_RING - 1)) * slot_n;
+      const int a = tt & (BW_AUX - 1);
+      double lam = lane < Ds ? s_lam0[a][lane] : 0.0;
+      double lu = lane < Du ? slot[o_gi + lane] : 0.0;
+      if (tt < H - 1) {
+        // lx[d] = sum_e ld_e J[e][d], lane d
+        if (lane < D || D > 32) {
+          for (int d = lane; d < D; d += 32) {
+            double lx = 0.0;
+            for (int e = 0; e < E; e++) {
+              const double ld = (mdl.kind == 1) ? s_lnext[mdl.vel_idx[e]] + 0.5 * mdl.T * s_lnext[mdl.pos_idx[e]] : s_lnext[e];
+              lx = fma(ld, slot[o_J + (size_t)e * D + d], lx);
+            }
+            s_lx[d] = lx;
+          }
+        }
+        for (int e = 0; e < E; e++) {
+          if (mdl.kind == 1) {
+            const int iv = mdl.vel_idx[e], ip = mdl.pos_idx[e];
+            if (lane == iv) lam += s_lnext[iv] + mdl.T * s_lnext[ip];
+            if (lane == ip) lam += s_lnext[ip];
+          } else if (lane == e) {
+            lam += s_lnext[e];
+          }
+        }
+        __syncwarp();
+        if (mdl.use_trig) {
+          for (int i = 0; i < mdl.n_na; i++)
+            if (lane == mdl.na_idx[i]) lam += s_lx[i];
+          for (int i = 0; i < mdl.n_a; i++)
+            if (lane == mdl.a_idx[i]) lam += s_lx[mdl.n_na + i] * s_mcos[a][i] - s_lx[mdl.n_na + mdl.n_a + i] * s_msin[a][i];
+          if (lane < Du) lu += s_lx[mdl.n_na + 2 * mdl.n_a + lane];
+        } else {
+          if (lane < Ds) lam += s_lx[lane];
+          if (lane < Du) lu += s_lx[Ds + lane];
+        }
+      }
+      double la = 0.0;
+      if (lane < Du) {
+        la = lu;
+        if (pol.squash) { double q = slot[o_u + lane] / pol.u_max[lane]; la *= (1.0 - q * q); }
+        s_la[lane] = la;
+        gbias += la;
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, la != 0.0);
+      if (lane == 0) s_active = act != 0u;
+      return lam;
+    };
+
+    // ---- pipeline fill ----------------------------------------------------------------------------------------------------------
+    double lam = 0.0, h = 0.0;   // chain: adjoint of x_t after stage A; basis: activation at the chain's current step
+    double lnv = 0.0, lmv = 0.0, lnp = 0.0;  // 4PMS carried adjoints of position pair i, replicated... (lane i of the chain warp)
+    if (chain) {
+      if (lane < Ds) s_lnext[lane] = 0.0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < BW_LAG; k++) issue(H - 1 - k);
+      cp_async_wait<BW_LAG - 2>();  // steps H-1 and H-2 have landed
+    }
+    __syncthreads();
+    if (!chain) { aux(H - 1); aux(H - 2); }
+    __syncthreads();
+    if (chain) {
+      lam = chain_A(H - 1);
+    } else {
+      h = activation(H - 1);
+      cp_async_wait<2>();  // step H-3
+    }
+    __syncthreads();
+
     for (int t = H - 1; t >= 0; t--) {
-      // ---- stage 0: publish this step's (prefetched) checkpoint in shared memory, start fetching the previous step's ----
-      {
-        if (tid < Ds) {
-          s_x[tid] = pre_x;
-          s_px[tid] = pre_px;
-          s_gs[tid] = pre_gs;
-        }
-        if (tid < Du) {
-          s_u[tid] = pre_u;
-          s_gi[tid] = pre_gi;
-        }
-        if (t < H - 1) {
+      const double* z = s_z[t & (BW_AUX - 1)];
+      const bool active = s_active != 0;
+      // ---- basis threads: policy adjoint of step t, thread b owns basis function b ----
+      if (!chain && active) {
+        double lh = 0.0;
 #pragma unroll
-          for (int k = 0; k < JR; k++) {
-            const int i = tid + k * (int)blockDim.x;
-            if (i < E * D) s_J[i] = pre_J[k];
-          }
-        }
-      }
-      __syncthreads();
-      if (t > 0) prefetch(t - 1);
-      const double* x = s_x;
-      const double* px = s_px;
-      const double* u = s_u;
-      // ---- stage A: adjoint of x_t from cost and from the model step t -> t+1; adjoint of u_t ----
-      if (tid == 0) {
-        double lam[MCP_MAX_DS], lu[MCP_MAX_DU];
-        for (int j = 0; j < Ds; j++) lam[j] = s_gs[j];
-        for (int k = 0; k < Du; k++) lu[k] = s_gi[k];
-        if (cost_w != 0.0) cost_grad_add(r.cost, x, t, Ds, cost_w, lam);
-        if (t < H - 1) {
-          const double* J = s_J;
-          double lx[MCP_MAX_D];
-          for (int d = 0; d < D; d++) lx[d] = 0.0;
-          for (int e = 0; e < E; e++) {
-            double ld;
-            if (mdl.kind == 1) {
-              int iv = mdl.vel_idx[e], ip = mdl.pos_idx[e];
-              ld = s_lnext[iv] + 0.5 * mdl.T * s_lnext[ip];
-              lam[iv] += s_lnext[iv] + mdl.T * s_lnext[ip];
-              lam[ip] += s_lnext[ip];
-            } else {
-              ld = s_lnext[e];
-              lam[e] += s_lnext[e];
-            }
-            for (int d = 0; d < D; d++) lx[d] = fma(ld, J[(size_t)e * D + d], lx[d]);
-          }
-          if (mdl.use_trig) {
-            for (int i = 0; i < mdl.n_na; i++) lam[mdl.na_idx[i]] += lx[i];
-            for (int i = 0; i < mdl.n_a; i++) {
-              double sn, cs;
-              sincos(x[mdl.a_idx[i]], &sn, &cs);
-              lam[mdl.a_idx[i]] += lx[mdl.n_na + i] * cs - lx[mdl.n_na + mdl.n_a + i] * sn;
-            }
-            for (int k = 0; k < Du; k++) lu[k] += lx[mdl.n_na + 2 * mdl.n_a + k];
-          } else {
-            for (int j = 0; j < Ds; j++) lam[j] += lx[j];
-            for (int k = 0; k < Du; k++) lu[k] += lx[Ds + k];
-          }
-        }
-        int act = 0;
-        for (int k = 0; k < Du; k++) {
-          double la = lu[k];
-          if (pol.squash) { double q = u[k] / pol.u_max[k]; la *= (1.0 - q * q); }
-          s_la[k] = la;
-          s_gbias[k] += la;
-          act |= (la != 0.0);
-        }
-        for (int j = 0; j < Ds; j++) s_lam[j] = lam[j];
-        s_active = act;
-      }
-      if (tid < Dp) s_z[tid] = policy_feature(pol, px, t, tid);
-      __syncthreads();
-      // ---- stage B: policy backward, thread b owns basis function b ----
-      if (s_active) {
-        double ld_b = 0.0;
-        if (has_b) {
-          double d = 0.0;
-#pragma unroll
-          for (int j = 0; j < DPT; j++)
-            if (j < Dp) { double q = (s_z[j] - cb[j]) * s_il[j]; d = fma(q, q, d); }
-          double h = exp(-d);
-          if (drop) h = keep_unit(r.noise, M, nb, t, t, m, b) ? h * keep_scale : 0.0;
-          double lh = 0.0;
-#pragma unroll
-          for (int k = 0; k < DUT; k++)
-            if (k < Du) { gw[k] = fma(s_la[k], h, gw[k]); lh = fma(s_la[k], wb[k], lh); }
-          ld_b = -h * lh;
-        }
+        for (int k = 0; k < DUT; k++)
+          if (k < Du) { gw[k] = fma(s_la[k], h, gw[k]); lh = fma(s_la[k], wb[k], lh); }
+        const double ld_b = -h * lh;
 #pragma unroll
         for (int j = 0; j < DPT; j++) {
           if (j < Dp) {
-            double cz = ld_b * 2.0 * (s_z[j] - cb[j]) * s_il[j] * s_il[j];  // d/dz_j ; d/dc_bj = -cz
+            double cz = ld_b * 2.0 * (z[j] - cb[j]) * s_il[j] * s_il[j];  // d/dz_j ; d/dc_bj = -cz
             gc[j] -= cz;
             double v = warp_sum(cz);
             if (lane == 0) s_red[warp][j] = v;
           }
         }
-        __syncthreads();
-        if (tid < Dp) {
-          double v = 0.0;
-          for (int w2 = 0; w2 < nwarp; w2++) v += s_red[w2][tid];
-          s_lz[tid] = v;
-          s_glz[tid] -= s_z[tid] * v;  // log-lengthscale gradient, first half (see below)
-        }
-        __syncthreads();
       }
-      // ---- stage C: adjoint of the policy input -> adjoint of x_t (through the measurement model if any) ----
-      if (tid == 0) {
-        double lp[MCP_MAX_DS];
-        for (int j = 0; j < Ds; j++) lp[j] = 0.0;
-        if (s_active) {
+      __syncthreads();  // Z
+      if (chain) {
+        // ---- adjoint of the policy input -> adjoint of x_t (through the measurement model if any) ----
+        double lz = 0.0;
+        if (active && lane < Dp) {
+          for (int w2 = 0; w2 < nbw; w2++) lz += s_red[w2][lane];
+          glz -= z[lane] * lz;  // log-lengthscale gradient, first half (see below)
+        }
+        if (lane < Dp) s_lz[lane] = lz;
+        __syncwarp();
+        double lp = 0.0;
+        if (active) {
+          const int a = t & (BW_AUX - 1);
           if (pol.kind == 1) {
-            for (int i = 0; i < pol.n_na; i++) lp[pol.na_idx[i]] += s_lz[i] * pol.inv_scale[i];
-            for (int i = 0; i < pol.n_a; i++) {
-              double sn, cs;
-              sincos(px[pol.a_idx[i]], &sn, &cs);
-              lp[pol.a_idx[i]] += -s_lz[pol.n_na + i] * pol.inv_scale[pol.n_na + i] * sn +
-                                  s_lz[pol.n_na + pol.n_a + i] * pol.inv_scale[pol.n_na + pol.n_a + i] * cs;
-            }
+            for (int i = 0; i < pol.n_na; i++)
+              if (lane == pol.na_idx[i]) lp += s_lz[i] * pol.inv_scale[i];
+            for (int i = 0; i < pol.n_a; i++)
+              if (lane == pol.a_idx[i])
+                lp += -s_lz[pol.n_na + i] * pol.inv_scale[pol.n_na + i] * s_psin[a][i] +
+                      s_lz[pol.n_na + pol.n_a + i] * pol.inv_scale[pol.n_na + pol.n_a + i] * s_pcos[a][i];
           } else if (pol.kind == 2) {
-            for (int j = 0; j < Ds; j++) lp[j] += s_lz[j] * pol.inv_scale[j] - s_lz[Ds + j] * pol.inv_scale[Ds + j];
+            if (lane < Ds) lp += s_lz[lane] * pol.inv_scale[lane] - s_lz[Ds + lane] * pol.inv_scale[Ds + lane];
           } else {
-            for (int j = 0; j < Ds; j++) lp[j] += s_lz[j] * pol.inv_scale[j];
+            if (lane < Ds) lp += s_lz[lane] * pol.inv_scale[lane];
           }
         }
         if (ms.enabled) {
-          for (int i = 0; i < ms.n_pos; i++) {
-            int ip = ms.pos_idx[i], iv = ms.vel_idx[i];
-            double lnp = s_lnp[i] + lp[ip], lmv = s_lmv[i] + lp[iv], lnv = s_lnv[i];
-            lp[ip] = 0.0;
-            lp[iv] = 0.0;
+          for (int i = 0; i < ms.n_pos; i++) {   // lane i carries the filter adjoints of pair i
+            const int ip = ms.pos_idx[i], iv = ms.vel_idx[i];
+            const double c_lnv = __shfl_sync(0xffffffffu, lnv, i), c_lmv = __shfl_sync(0xffffffffu, lmv, i), c_lnp = __shfl_sync(0xffffffffu, lnp, i);
+            double a_lnp = c_lnp + __shfl_sync(0xffffffffu, lp, ip), a_lmv = c_lmv + __shfl_sync(0xffffffffu, lp, iv), a_lnv = c_lnv;
+            if (lane == ip || lane == iv) lp = 0.0;
             if (t > 0) {
-              lnv += ms.b0 / ms.a0 * lmv;
-              s_lnv[i] = ms.b1 / ms.a0 * lmv;   // carried to nv_{t-1}
-              s_lmv[i] = -ms.a1 / ms.a0 * lmv;  // carried to mv_{t-1}
-              lnp += lnv / ms.T;
-              s_lnp[i] = -lnv / ms.T;           // carried to np_{t-1}
-              s_lam[ip] += lnp;
+              a_lnv += ms.b0 / ms.a0 * a_lmv;
+              const double n_lnv = ms.b1 / ms.a0 * a_lmv;   // carried to nv_{t-1}
+              const double n_lmv = -ms.a1 / ms.a0 * a_lmv;  // carried to mv_{t-1}
+              a_lnp += a_lnv / ms.T;
+              const double n_lnp = -a_lnv / ms.T;           // carried to np_{t-1}
+              if (lane == i) { lnv = n_lnv; lmv = n_lmv; lnp = n_lnp; }
+              if (lane == ip) lam += a_lnp;
             } else {
-              s_lam[ip] += lnp;
-              s_lam[iv] += lnv + lmv;
+              if (lane == ip) lam += a_lnp;
+              if (lane == iv) lam += a_lnv + a_lmv;
             }
           }
         }
-        for (int j = 0; j < Ds; j++) { s_lam[j] += lp[j]; s_lnext[j] = s_lam[j]; }
+        lam += lp;
+        if (lane < Ds) s_lnext[lane] = lam;
+        __syncwarp();
+        if (t > 0) lam = chain_A(t - 1);
+      } else {
+        // ---- ahead of the chain: activation of step t-1, derived quantities of step t-2, checkpoint of step t-5 ----
+        h = activation(t - 1);
+        aux(t - 2);
+        issue(t - BW_LAG);
+        cp_async_wait<2>();  // the checkpoint aux() reads one iteration from now has landed
       }
-      __syncthreads();
+      __syncthreads();  // Y
     }
-    if (g_x0 != nullptr && tid < Ds) g_x0[(size_t)m * Ds + tid] = s_lnext[tid];
-    __syncthreads();
+    if (chain && g_x0 != nullptr && lane < Ds) g_x0[(size_t)m * Ds + lane] = lam;
   }
 
   // ---- per-CTA partial gradients: [g_log_ls (Dp) | g_centers (nb*Dp) | g_W (Du*nb) | g_bias (Du)] ----
   // d/dlog l_j of ((z_j-c_bj)/l_j)^2 = -2 ((z_j-c_bj)/l_j)^2, hence
   //   g_logls_j = sum_steps sum_b [d/dc_bj contribution] (z_j - c_bj) = -sum_steps z_j lz_j - sum_b c_bj g_c[b][j]
   double* P = partials + (size_t)blockIdx.x * (Dp + (size_t)nb * Dp + (size_t)Du * nb + Du);
+  if (!chain) {
 #pragma unroll
-  for (int j = 0; j < DPT; j++) {
-    if (j < Dp) {
-      double v = warp_sum(cb[j] * gc[j]);
-      if (lane == 0) s_red[warp][j] = v;
+    for (int j = 0; j < DPT; j++) {
+      if (j < Dp) {
+        double v = warp_sum(cb[j] * gc[j]);
+        if (lane == 0) s_red[warp][j] = v;
+      }
     }
   }
   __syncthreads();
-  if (tid < Dp) {
-    double v = 0.0;
-    for (int w2 = 0; w2 < nwarp; w2++) v += s_red[w2][tid];
-    P[tid] = s_glz[tid] - v;
+  if (chain) {
+    if (lane < Dp) {
+      double v = 0.0;
+      for (int w2 = 0; w2 < nbw; w2++) v += s_red[w2][lane];
+      P[lane] = glz - v;
+    }
+    if (lane < Du) P[Dp + (size_t)nb * Dp + (size_t)Du * nb + lane] = gbias;
   }
   if (has_b) {
 #pragma unroll
@@ -619,7 +676,6 @@ __global__ void __launch_bounds__(512) rollout_bwd_kernel(const __grid_constant_
     for (int k = 0; k < DUT; k++)
       if (k < Du) P[Dp + (size_t)nb * Dp + (size_t)k * nb + b] = gw[k];
   }
-  if (tid < Du) P[Dp + (size_t)nb * Dp + (size_t)Du * nb + tid] = s_gbias[tid];
 }
 
 // out[i] = sum over CTAs of partials[cta][i] (fixed order -> bit-stable)
@@ -865,8 +921,14 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_bwd(const 
   if (int e = carve(r, w)) return e;
   const int nb = r->policy.nb, Dp = r->policy.Dp, Du = r->policy.Du;
   const int nparam = Dp + nb * Dp + Du * nb + Du;
-  const int threads = (nb + 31) / 32 * 32;
-#define MCP_BWD(DPT, DUT) rollout_bwd_kernel<DPT, DUT><<<w.bwd_ctas, threads, 0, st>>>(*r, *g, w.partials, g->g_x0)
+  const int threads = (nb + 31) / 32 * 32 + 32;  // one thread per basis function + the chain warp
+  const size_t ring = (size_t)BW_RING * (3 * r->model.Ds + 2 * Du + r->model.E * r->model.D) * sizeof(double);  // <= 37 KB
+  // up to 224 basis functions: 256 threads and three resident CTAs per SM (the reference's 400 particles are one wave); else 544 threads
+#define MCP_BWD(DPT, DUT)                                                                                          \
+  do {                                                                                                             \
+    if (threads <= 256) rollout_bwd_kernel<DPT, DUT, 256, 3><<<w.bwd_ctas, threads, ring, st>>>(*r, *g, w.partials, g->g_x0); \
+    else rollout_bwd_kernel<DPT, DUT, 544, 1><<<w.bwd_ctas, threads, ring, st>>>(*r, *g, w.partials, g->g_x0);    \
+  } while (0)
   if (Dp <= 8) { if (Du <= 2) MCP_BWD(8, 2); else MCP_BWD(8, 8); }
   else if (Dp <= 16) { if (Du <= 2) MCP_BWD(16, 2); else MCP_BWD(16, 8); }
   else { if (Du <= 2) MCP_BWD(32, 2); else MCP_BWD(32, 8); }
