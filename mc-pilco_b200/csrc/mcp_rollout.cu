@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
   __shared__ double s_il[MCP_MAX_DP];
   __shared__ double s_z[BW_AUX][MCP_MAX_DP], s_lam0[BW_AUX][MCP_MAX_DS];
   __shared__ double s_msin[BW_AUX][MCP_MAX_DS], s_mcos[BW_AUX][MCP_MAX_DS], s_psin[BW_AUX][MCP_MAX_DS], s_pcos[BW_AUX][MCP_MAX_DS];
-  __shared__ double s_lnext[MCP_MAX_DS], s_lx[MCP_MAX_D], s_la[MCP_MAX_DU], s_lz[MCP_MAX_DP];
+  __shared__ double s_lnext[MCP_MAX_DS], s_ld[MCP_MAX_E], s_lx[MCP_MAX_D], s_la[MCP_MAX_DU], s_lz[MCP_MAX_DP];
   __shared__ double s_red[16][MCP_MAX_DP];
   __shared__ int s_active;
 
@@ -427,6 +427,32 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
   const double* polin = (ms.enabled && r.pol_in) ? r.pol_in : r.states;
   // chain-warp registers: lane j carries component j
   double glz = 0.0, gbias = 0.0;  // log-lengthscale gradient (first half, see below), bias gradient
+  // where component `lane` of the state sits in the index lists of the model and the policy (-1: nowhere; the lists hold each state
+  // component at most once), looked up once so that the per-step chain has no loops over them
+  int c_vel = -1, c_pos = -1, c_partner = 0, c_mna = -1, c_ma = -1, c_pna = -1, c_pa = -1, e_iv = 0, e_ip = 0;
+  double c_isc0 = 0.0, c_isc1 = 0.0, c_isc2 = 0.0, c_umax = 1.0;
+  if (chain) {
+    if (mdl.kind == 1) {
+      for (int e = 0; e < E; e++) {
+        if (mdl.vel_idx[e] == lane) { c_vel = e; c_partner = mdl.pos_idx[e]; }
+        if (mdl.pos_idx[e] == lane) c_pos = e;
+      }
+      if (lane < E) { e_iv = mdl.vel_idx[lane]; e_ip = mdl.pos_idx[lane]; }
+    }
+    if (mdl.use_trig) {
+      for (int i = 0; i < mdl.n_na; i++) if (mdl.na_idx[i] == lane) c_mna = i;
+      for (int i = 0; i < mdl.n_a; i++) if (mdl.a_idx[i] == lane) c_ma = i;
+    }
+    if (pol.kind == 1) {
+      for (int i = 0; i < pol.n_na; i++) if (pol.na_idx[i] == lane) { c_pna = i; c_isc0 = pol.inv_scale[i]; }
+      for (int i = 0; i < pol.n_a; i++)
+        if (pol.a_idx[i] == lane) { c_pa = i; c_isc1 = pol.inv_scale[pol.n_na + i]; c_isc2 = pol.inv_scale[pol.n_na + pol.n_a + i]; }
+    } else if (lane < Ds) {
+      c_isc0 = pol.inv_scale[lane];
+      if (pol.kind == 2) c_isc1 = pol.inv_scale[Ds + lane];
+    }
+    if (lane < Du && pol.squash) c_umax = pol.u_max[lane];
+  }
   __syncthreads();
 
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
@@ -499,32 +525,24 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
       double lam = lane < Ds ? s_lam0[a][lane] : 0.0;
       double lu = lane < Du ? slot[o_gi + lane] : 0.0;
       if (tt < H - 1) {
-        // lx[d] = sum_e ld_e J[e][d], lane d
-        if (lane < D || D > 32) {
-          for (int d = lane; d < D; d += 32) {
-            double lx = 0.0;
-            for (int e = 0; e < E; e++) {
-              const double ld = (mdl.kind == 1) ? s_lnext[mdl.vel_idx[e]] + 0.5 * mdl.T * s_lnext[mdl.pos_idx[e]] : s_lnext[e];
-              lx = fma(ld, slot[o_J + (size_t)e * D + d], lx);
-            }
-            s_lx[d] = lx;
-          }
+        // adjoint of the GP output e (lane e) -> s_ld; lx[d] = sum_e ld_e J[e][d] (lane d) -> s_lx
+        if (lane < E) s_ld[lane] = (mdl.kind == 1) ? s_lnext[e_iv] + 0.5 * mdl.T * s_lnext[e_ip] : s_lnext[lane];
+        __syncwarp();
+        for (int d = lane; d < D; d += 32) {
+          double lx = 0.0;
+          for (int e = 0; e < E; e++) lx = fma(s_ld[e], slot[o_J + e * D + d], lx);
+          s_lx[d] = lx;
         }
-        for (int e = 0; e < E; e++) {
-          if (mdl.kind == 1) {
-            const int iv = mdl.vel_idx[e], ip = mdl.pos_idx[e];
-            if (lane == iv) lam += s_lnext[iv] + mdl.T * s_lnext[ip];
-            if (lane == ip) lam += s_lnext[ip];
-          } else if (lane == e) {
-            lam += s_lnext[e];
-          }
+        if (mdl.kind == 1) {
+          if (c_vel >= 0) lam += s_lnext[lane] + mdl.T * s_lnext[c_partner];
+          if (c_pos >= 0) lam += s_lnext[lane];
+        } else if (lane < E) {
+          lam += s_lnext[lane];
         }
         __syncwarp();
         if (mdl.use_trig) {
-          for (int i = 0; i < mdl.n_na; i++)
-            if (lane == mdl.na_idx[i]) lam += s_lx[i];
-          for (int i = 0; i < mdl.n_a; i++)
-            if (lane == mdl.a_idx[i]) lam += s_lx[mdl.n_na + i] * s_mcos[a][i] - s_lx[mdl.n_na + mdl.n_a + i] * s_msin[a][i];
+          if (c_mna >= 0) lam += s_lx[c_mna];
+          if (c_ma >= 0) lam += s_lx[mdl.n_na + c_ma] * s_mcos[a][c_ma] - s_lx[mdl.n_na + mdl.n_a + c_ma] * s_msin[a][c_ma];
           if (lane < Du) lu += s_lx[mdl.n_na + 2 * mdl.n_a + lane];
         } else {
           if (lane < Ds) lam += s_lx[lane];
@@ -534,7 +552,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
       double la = 0.0;
       if (lane < Du) {
         la = lu;
-        if (pol.squash) { double q = slot[o_u + lane] / pol.u_max[lane]; la *= (1.0 - q * q); }
+        if (pol.squash) { double q = slot[o_u + lane] / c_umax; la *= (1.0 - q * q); }
         s_la[lane] = la;
         gbias += la;
       }
@@ -598,16 +616,12 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
         if (active) {
           const int a = t & (BW_AUX - 1);
           if (pol.kind == 1) {
-            for (int i = 0; i < pol.n_na; i++)
-              if (lane == pol.na_idx[i]) lp += s_lz[i] * pol.inv_scale[i];
-            for (int i = 0; i < pol.n_a; i++)
-              if (lane == pol.a_idx[i])
-                lp += -s_lz[pol.n_na + i] * pol.inv_scale[pol.n_na + i] * s_psin[a][i] +
-                      s_lz[pol.n_na + pol.n_a + i] * pol.inv_scale[pol.n_na + pol.n_a + i] * s_pcos[a][i];
+            if (c_pna >= 0) lp += s_lz[c_pna] * c_isc0;
+            if (c_pa >= 0) lp += -s_lz[pol.n_na + c_pa] * c_isc1 * s_psin[a][c_pa] + s_lz[pol.n_na + pol.n_a + c_pa] * c_isc2 * s_pcos[a][c_pa];
           } else if (pol.kind == 2) {
-            if (lane < Ds) lp += s_lz[lane] * pol.inv_scale[lane] - s_lz[Ds + lane] * pol.inv_scale[Ds + lane];
+            if (lane < Ds) lp += s_lz[lane] * c_isc0 - s_lz[Ds + lane] * c_isc1;
           } else {
-            if (lane < Ds) lp += s_lz[lane] * pol.inv_scale[lane];
+            if (lane < Ds) lp += s_lz[lane] * c_isc0;
           }
         }
         if (ms.enabled) {
