@@ -393,6 +393,26 @@ __global__ void cost_final_kernel(int M, int H, const double* __restrict__ stats
 // ------------------------------------------------------------------------------------------------
 constexpr int BW_RING = 8, BW_AUX = 4, BW_LAG = 5;
 
+// Sums N = 8 / 16 / 32 per-lane values over the warp with N - 1 + (5 - log2 N) shuffles instead of 5 N: each butterfly level halves the
+// number of values a lane still carries.  Afterwards v[0] of lane l holds the warp total of value l >> (5 - log2 N) (the lanes that share
+// those upper bits all hold it).  Fixed order, so the result is reproducible.
+template <int N>
+__device__ __forceinline__ void warp_sum_multi(double (&v)[N], int lane) {
+  static_assert(N == 8 || N == 16 || N == 32, "warp_sum_multi: 8, 16 or 32 values");
+  int offset = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, offset >>= 1) {
+    const bool hi = (lane & offset) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; j++) {
+      const double send = hi ? v[j] : v[j + n / 2], keep = hi ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+    }
+  }
+#pragma unroll
+  for (; offset >= 1; offset >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], offset);
+}
+
 template <int DPT, int DUT, int NT, int NCTA>
 __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_constant__ McpRollout r, const __grid_constant__ McpRolloutGrad g,
                                                            double* __restrict__ partials, double* __restrict__ g_x0) {
@@ -411,7 +431,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
   __shared__ double s_il[MCP_MAX_DP];
   __shared__ double s_z[BW_AUX][MCP_MAX_DP], s_lam0[BW_AUX][MCP_MAX_DS];
   __shared__ double s_msin[BW_AUX][MCP_MAX_DS], s_mcos[BW_AUX][MCP_MAX_DS], s_psin[BW_AUX][MCP_MAX_DS], s_pcos[BW_AUX][MCP_MAX_DS];
-  __shared__ double s_lnext[MCP_MAX_DS], s_ld[MCP_MAX_E], s_lx[MCP_MAX_D], s_la[MCP_MAX_DU], s_lz[MCP_MAX_DP];
+  __shared__ double s_la[MCP_MAX_DU];
   __shared__ double s_red[16][MCP_MAX_DP];
   __shared__ int s_active;
 
@@ -462,7 +482,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
       if (tt >= 0) {
         double* slot = bw_ring + (size_t)(tt & (BW_RING - 1)) * slot_n;
         const size_t row = (size_t)tt * M + m;
-        for (int i = tid; i < slot_n; i += nbt) {
+        for (int i = (tid >= nbt - 32) ? tid - (nbt - 32) : tid + 32; i < slot_n; i += nbt) {  // the last basis warp first: warp 0 has the heaviest role above
           const double* src = nullptr;
           if (i < o_px) src = r.states + row * Ds + i;
           else if (i < o_gs) src = polin + row * Ds + (i - o_px);
@@ -482,7 +502,8 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
       const int a = tt & (BW_AUX - 1);
       const int n_ma = mdl.use_trig ? mdl.n_a : 0, n_pa = (pol.kind == 1) ? pol.n_a : 0;
       const int nroles = Dp + 1 + n_ma + n_pa;
-      for (int role = tid; role < nroles; role += nbt) {
+      // role r -> lane r / nbw of warp r % nbw: the divergent roles (cos / sin / cost gradient) run in different warps, in parallel
+      for (int role = lane * nbw + warp; role < nroles; role += nbt) {
         if (role < Dp) {
           s_z[a][role] = policy_feature(pol, slot + o_px, tt, role);
         } else if (role == Dp) {  // adjoint of x_tt from the caller's gradient and the fused cost
@@ -519,34 +540,40 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
     };
     // chain warp, stage A of step tt: adjoint of x_tt from the cost and from the model step tt -> tt+1 (lane j: component j, returned);
     // adjoint of u_tt -> s_la, s_active
-    auto chain_A = [&](int tt) {
+    // (everything the lanes exchange goes through shuffles: ln is the adjoint x_{tt+1} received, component `lane`)
+    auto chain_A = [&](int tt, double ln) {
       const double* slot = bw_ring + (size_t)(tt & (BW_RING - 1)) * slot_n;
       const int a = tt & (BW_AUX - 1);
       double lam = lane < Ds ? s_lam0[a][lane] : 0.0;
       double lu = lane < Du ? slot[o_gi + lane] : 0.0;
       if (tt < H - 1) {
-        // adjoint of the GP output e (lane e) -> s_ld; lx[d] = sum_e ld_e J[e][d] (lane d) -> s_lx
-        if (lane < E) s_ld[lane] = (mdl.kind == 1) ? s_lnext[e_iv] + 0.5 * mdl.T * s_lnext[e_ip] : s_lnext[lane];
-        __syncwarp();
-        for (int d = lane; d < D; d += 32) {
-          double lx = 0.0;
-          for (int e = 0; e < E; e++) lx = fma(s_ld[e], slot[o_J + e * D + d], lx);
-          s_lx[d] = lx;
-        }
+        // adjoint of the GP output e in lane e; lx[d] = sum_e ld_e J[e][d] in lane d
+        double ld = ln;
         if (mdl.kind == 1) {
-          if (c_vel >= 0) lam += s_lnext[lane] + mdl.T * s_lnext[c_partner];
-          if (c_pos >= 0) lam += s_lnext[lane];
+          const double a_v = __shfl_sync(0xffffffffu, ln, e_iv), a_p = __shfl_sync(0xffffffffu, ln, e_ip);
+          ld = a_v + 0.5 * mdl.T * a_p;
+          const double part = __shfl_sync(0xffffffffu, ln, c_partner);
+          if (c_vel >= 0) lam += ln + mdl.T * part;
+          if (c_pos >= 0) lam += ln;
         } else if (lane < E) {
-          lam += s_lnext[lane];
+          lam += ln;
         }
-        __syncwarp();
+        double lx = 0.0;
+        const double* Jd = slot + o_J + (lane < D ? lane : 0);
+        for (int e = 0; e < E; e++) lx = fma(__shfl_sync(0xffffffffu, ld, e), Jd[e * D], lx);
         if (mdl.use_trig) {
-          if (c_mna >= 0) lam += s_lx[c_mna];
-          if (c_ma >= 0) lam += s_lx[mdl.n_na + c_ma] * s_mcos[a][c_ma] - s_lx[mdl.n_na + mdl.n_a + c_ma] * s_msin[a][c_ma];
-          if (lane < Du) lu += s_lx[mdl.n_na + 2 * mdl.n_a + lane];
+          const int n_na = mdl.n_na, n_a = mdl.n_a;
+          const double x_na = __shfl_sync(0xffffffffu, lx, c_mna >= 0 ? c_mna : 0);
+          const double x_c = __shfl_sync(0xffffffffu, lx, (n_na + (c_ma >= 0 ? c_ma : 0)) & 31);
+          const double x_s = __shfl_sync(0xffffffffu, lx, (n_na + n_a + (c_ma >= 0 ? c_ma : 0)) & 31);
+          const double x_u = __shfl_sync(0xffffffffu, lx, (n_na + 2 * n_a + lane) & 31);
+          if (c_mna >= 0) lam += x_na;
+          if (c_ma >= 0) lam += x_c * s_mcos[a][c_ma] - x_s * s_msin[a][c_ma];
+          if (lane < Du) lu += x_u;
         } else {
-          if (lane < Ds) lam += s_lx[lane];
-          if (lane < Du) lu += s_lx[Ds + lane];
+          const double x_u = __shfl_sync(0xffffffffu, lx, (Ds + lane) & 31);
+          if (lane < Ds) lam += lx;
+          if (lane < Du) lu += x_u;
         }
       }
       double la = 0.0;
@@ -564,9 +591,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
     // ---- pipeline fill ----------------------------------------------------------------------------------------------------------
     double lam = 0.0, h = 0.0;   // chain: adjoint of x_t after stage A; basis: activation at the chain's current step
     double lnv = 0.0, lmv = 0.0, lnp = 0.0;  // 4PMS carried adjoints of position pair i, replicated... (lane i of the chain warp)
-    if (chain) {
-      if (lane < Ds) s_lnext[lane] = 0.0;
-    } else {
+    if (!chain) {
 #pragma unroll
       for (int k = 0; k < BW_LAG; k++) issue(H - 1 - k);
       cp_async_wait<BW_LAG - 2>();  // steps H-1 and H-2 have landed
@@ -575,7 +600,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
     if (!chain) { aux(H - 1); aux(H - 2); }
     __syncthreads();
     if (chain) {
-      lam = chain_A(H - 1);
+      lam = chain_A(H - 1, 0.0);
     } else {
       h = activation(H - 1);
       cp_async_wait<2>();  // step H-3
@@ -592,15 +617,15 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
         for (int k = 0; k < DUT; k++)
           if (k < Du) { gw[k] = fma(s_la[k], h, gw[k]); lh = fma(s_la[k], wb[k], lh); }
         const double ld_b = -h * lh;
+        double cz[DPT];
 #pragma unroll
         for (int j = 0; j < DPT; j++) {
-          if (j < Dp) {
-            double cz = ld_b * 2.0 * (z[j] - cb[j]) * s_il[j] * s_il[j];  // d/dz_j ; d/dc_bj = -cz
-            gc[j] -= cz;
-            double v = warp_sum(cz);
-            if (lane == 0) s_red[warp][j] = v;
-          }
+          cz[j] = (j < Dp) ? ld_b * 2.0 * (z[j] - cb[j]) * s_il[j] * s_il[j] : 0.0;  // d/dz_j ; d/dc_bj = -cz
+          gc[j] -= cz[j];
         }
+        warp_sum_multi<DPT>(cz, lane);
+        constexpr int SH = DPT == 8 ? 2 : (DPT == 16 ? 1 : 0);
+        if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < Dp) s_red[warp][lane >> SH] = cz[0];
       }
       __syncthreads();  // Z
       if (chain) {
@@ -610,18 +635,21 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
           for (int w2 = 0; w2 < nbw; w2++) lz += s_red[w2][lane];
           glz -= z[lane] * lz;  // log-lengthscale gradient, first half (see below)
         }
-        if (lane < Dp) s_lz[lane] = lz;
-        __syncwarp();
         double lp = 0.0;
-        if (active) {
+        {
           const int a = t & (BW_AUX - 1);
           if (pol.kind == 1) {
-            if (c_pna >= 0) lp += s_lz[c_pna] * c_isc0;
-            if (c_pa >= 0) lp += -s_lz[pol.n_na + c_pa] * c_isc1 * s_psin[a][c_pa] + s_lz[pol.n_na + pol.n_a + c_pa] * c_isc2 * s_pcos[a][c_pa];
+            const int n_na = pol.n_na, n_a = pol.n_a;
+            const double z_na = __shfl_sync(0xffffffffu, lz, c_pna >= 0 ? c_pna : 0);
+            const double z_c = __shfl_sync(0xffffffffu, lz, (n_na + (c_pa >= 0 ? c_pa : 0)) & 31);
+            const double z_s = __shfl_sync(0xffffffffu, lz, (n_na + n_a + (c_pa >= 0 ? c_pa : 0)) & 31);
+            if (c_pna >= 0) lp += z_na * c_isc0;
+            if (c_pa >= 0) lp += -z_c * c_isc1 * s_psin[a][c_pa] + z_s * c_isc2 * s_pcos[a][c_pa];
           } else if (pol.kind == 2) {
-            if (lane < Ds) lp += s_lz[lane] * c_isc0 - s_lz[Ds + lane] * c_isc1;
+            const double z_t = __shfl_sync(0xffffffffu, lz, (Ds + lane) & 31);
+            if (lane < Ds) lp += lz * c_isc0 - z_t * c_isc1;
           } else {
-            if (lane < Ds) lp += s_lz[lane] * c_isc0;
+            if (lane < Ds) lp += lz * c_isc0;
           }
         }
         if (ms.enabled) {
@@ -644,10 +672,8 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
             }
           }
         }
-        lam += lp;
-        if (lane < Ds) s_lnext[lane] = lam;
-        __syncwarp();
-        if (t > 0) lam = chain_A(t - 1);
+        lam += lp;   // = adjoint of x_t, complete
+        if (t > 0) lam = chain_A(t - 1, lam);
       } else {
         // ---- ahead of the chain: activation of step t-1, derived quantities of step t-2, checkpoint of step t-5 ----
         h = activation(t - 1);
@@ -665,13 +691,12 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
   //   g_logls_j = sum_steps sum_b [d/dc_bj contribution] (z_j - c_bj) = -sum_steps z_j lz_j - sum_b c_bj g_c[b][j]
   double* P = partials + (size_t)blockIdx.x * (Dp + (size_t)nb * Dp + (size_t)Du * nb + Du);
   if (!chain) {
+    double cg[DPT];
 #pragma unroll
-    for (int j = 0; j < DPT; j++) {
-      if (j < Dp) {
-        double v = warp_sum(cb[j] * gc[j]);
-        if (lane == 0) s_red[warp][j] = v;
-      }
-    }
+    for (int j = 0; j < DPT; j++) cg[j] = cb[j] * gc[j];
+    warp_sum_multi<DPT>(cg, lane);
+    constexpr int SH = DPT == 8 ? 2 : (DPT == 16 ? 1 : 0);
+    if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < Dp) s_red[warp][lane >> SH] = cg[0];
   }
   __syncthreads();
   if (chain) {
