@@ -858,160 +858,209 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
   }
 }
 
-// Reduce for WIDE gp inputs (8 < D <= 32; the UR5 model has D = 24) with an SE term and at most one linear term: a lane cannot
-// hold 4 D accumulators, so the gradient sums are done in two stages per tile of 64 training points.  Stage 1, lanes over points:
-// kernel value, mean / q / E0 accumulators and the four per-point coefficients T[n] = (a e, v e, a, v) into shared memory.
-// Stage 2, lane j over its dimension and all four channels: acc[j][c] += Y[n][j] T[n][c] — no cross-lane reduction at all.
-//   sum_n a_n dk_n/dx_j = -2 ils_j^2 (x_j E0 - acc[j][a e]) + w1_j acc[j][a]        (and the same with v for the variance)
-// One warp per particle gives only E * M warps (1200 for UR5: 8 per SM, latency-bound at 67 us per step), so the training points are
-// split over the CTAs of a thread-block cluster (gridDim.z = cluster size = 1 or 2, chosen from N alone): each CTA reduces every
-// nseg-th tile, the partial sums meet in rank 0 through distributed shared memory in a fixed order (bit-stable), rank 0 finalises.
-// Four warps per CTA and clusters of two keep all CTAs of the UR5 shape resident in one wave (clusters of four with eight-warp CTAs
-// made 1.4 waves: 50 us).
+// Reduce for WIDE gp inputs (8 < D <= 32; the UR5 model has D = 24) with an SE term and at most one linear term.  Everything is small
+// here (UR5: 200 particles x 6 outputs x 400 training points), so the kernel is built to be short rather than wide:
+//   * the kernel VALUE is not evaluated again: the K* row the contraction consumed is read beside the V row, the linear term
+//     L1[p][n] = o + sum_j (w_j x_pj) y_nj of the CTA's 8 particles comes from one small DMMA product per tile, and the
+//     squared-exponential part is e_n = k_n - L1_n (no distance, no exp);
+//   * the gradient sums are ONE 8 x 8 x 4 DMMA chain per warp and feature tile: rows = the four weight channels (a e, v e, a, v) of the
+//     warp's two particles, columns = features [y_0 .. y_{D-1} | 1, k_A, k_B], contraction over the tile's 64 training points:
+//       sum_n a_n dk_n/dx_j = -2 ils_j^2 (x_j E0 - E1_j) + w1_j C1_j,  E1_j = [a e] x y_j,  E0 = [a e] x 1,  C1_j = [a] x y_j,
+//     and mean / q fall out of the same product as [a] x k, [v] x k;
+//   * the training points are split over the CTAs of a thread-block cluster (gridDim.z = cluster size = 1, 2 or 4, chosen from N alone):
+//     each CTA reduces every nseg-th tile, the partial sums meet in rank 0 through distributed shared memory in a fixed order
+//     (bit-stable), rank 0 finalises.  UR5: 25 x 6 x 4 = 600 CTAs of 128 threads, one wave.
 constexpr int WIDE_TILE = 64;
-constexpr int WIDE_WPC = 4;  // warps (= particles) per CTA: 128 threads, 6 resident CTAs per SM
-static inline int wide_segments(int N) { return cdiv(N, WIDE_TILE) >= 2 ? 2 : 1; }
+constexpr int WIDE_WPC = 4;              // warps per CTA
+constexpr int WIDE_PPC = 2 * WIDE_WPC;   // particles per CTA (two per warp: the two halves of the DMMA's eight rows)
+constexpr int WIDE_LDT = WIDE_TILE + 4;  // row stride = 4 (mod 16) doubles: conflict-free DMMA fragment loads, lane <-> point reads stride 1
+constexpr int WIDE_LDX = MCP_MAX_D + 4;
+constexpr int WIDE_LDG = MCP_MAX_D + 8;  // feature columns of the result tile: y tiles, then the special tile [1, k_A, k_B, 0 ...]
+static inline int wide_segments(int N) {
+  const int tiles = cdiv(N, WIDE_TILE);
+  return tiles >= 4 ? 4 : (tiles >= 2 ? 2 : 1);
+}
+static inline size_t wide_smem_bytes(int D) {
+  const int Dp8 = (D + 7) & ~7;
+  return sizeof(double) * ((size_t)WIDE_WPC * 10 * WIDE_LDT + WIDE_PPC * WIDE_LDT + WIDE_PPC * WIDE_LDX + WIDE_PPC * MCP_MAX_D + WIDE_TILE +
+                           MCP_MAX_D + (size_t)Dp8 * WIDE_LDT);
+}
 __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const double* __restrict__ Xs, int M, const double* __restrict__ Xtr,
-                                                 const double* __restrict__ alpha, int N, const double* __restrict__ V, int ldv,
-                                                 double var_scale, int E, int e, double* __restrict__ mean, double* __restrict__ var,
-                                                 double* __restrict__ jmean, double* __restrict__ jvar) {
+                                                 const double* __restrict__ alpha, int N, const double* __restrict__ Ks,
+                                                 const double* __restrict__ V, int ldv, double var_scale, int E, int e,
+                                                 double* __restrict__ mean, double* __restrict__ var, double* __restrict__ jmean,
+                                                 double* __restrict__ jvar) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int nseg = (int)cluster.num_blocks(), seg = (int)cluster.block_rank();
-  __shared__ double sY[WIDE_TILE][MCP_MAX_D + 1];  // +1: lanes over points read a column without bank conflicts
-  __shared__ double sA[WIDE_TILE];
-  __shared__ __align__(32) double sT[WIDE_WPC][WIDE_TILE][4];
-  __shared__ double sX[WIDE_WPC][MCP_MAX_D], sXw[WIDE_WPC][MCP_MAX_D];
-  __shared__ double sIl[MCP_MAX_D];
-  __shared__ __align__(32) double sG[WIDE_WPC][MCP_MAX_D][4];
-  __shared__ double sS[WIDE_WPC][4];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int m = min(blockIdx.x * WIDE_WPC + warp, M - 1);
-  const bool owner = blockIdx.x * WIDE_WPC + warp < M;
+  // dynamic shared memory (wide_smem_bytes(D): 44 KB at D = 24, so that five CTAs — all 600 of the UR5 step — share an SM)
+  extern __shared__ __align__(16) double wide_smem[];
+  const int Dp8 = (s.D + 7) & ~7;
+  double(*sW)[10][WIDE_LDT] = reinterpret_cast<double(*)[10][WIDE_LDT]>(wide_smem);  // per warp: 8 weight rows (4 channels x 2 particles), the two K* rows
+  double(*sL1)[WIDE_LDT] = reinterpret_cast<double(*)[WIDE_LDT]>(wide_smem + WIDE_WPC * 10 * WIDE_LDT);  // linear kernel term [particle][point]
+  double(*sXw)[WIDE_LDX] = reinterpret_cast<double(*)[WIDE_LDX]>(&sL1[WIDE_PPC][0]);                     // w1_j x_pj
+  double(*sX)[MCP_MAX_D] = reinterpret_cast<double(*)[MCP_MAX_D]>(&sXw[WIDE_PPC][0]);
+  double* sA = &sX[WIDE_PPC][0];
+  double* sIl = sA + WIDE_TILE;
+  double(*sYt)[WIDE_LDT] = reinterpret_cast<double(*)[WIDE_LDT]>(sIl + MCP_MAX_D);  // [Dp8][LDT] training inputs of the tile, transposed
+  static_assert(8 * WIDE_LDG <= 10 * WIDE_LDT, "the result tile reuses the warp's weight rows");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x, gq = lane >> 2, q = lane & 3;
   const int D = s.D, np1 = s.n_poly;  // np1 in {0, 1}
-  const double off = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0, lam = s.lambda;
+  const double off = np1 ? s.poly_w2[0][0][MCP_MAX_D] : 0.0;
   const bool se = s.has_se != 0;
-  if (lane < D) {
-    const double xj = Xs[(size_t)m * D + lane];
-    sX[warp][lane] = xj;
-    sXw[warp][lane] = np1 ? s.poly_w2[0][0][lane] * xj : 0.0;
+  const int nfy = (D + 7) >> 3;       // feature tiles of training inputs; tile nfy is the special one
+  const int p0 = blockIdx.x * WIDE_PPC;
+  for (int el = tid; el < WIDE_PPC * WIDE_LDX; el += WIDE_WPC * 32) {
+    const int p = el / WIDE_LDX, j = el - p * WIDE_LDX;
+    const double xj = (j < D && p0 + p < M) ? Xs[(size_t)(p0 + p) * D + j] : 0.0;
+    sXw[p][j] = (np1 && j < D) ? s.poly_w2[0][0][j] * xj : 0.0;
+    if (j < MCP_MAX_D) sX[p][j] = xj;
   }
   if (tid < MCP_MAX_D) sIl[tid] = tid < D ? s.inv_ls[tid] : 0.0;
-  double mu = 0.0, q = 0.0, E0a = 0.0, E0v = 0.0;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // lane j < D: channels (a e, v e, a, v) of dimension j
-  const double* v = V + (size_t)m * ldv;
+  for (int el = tid; el < (Dp8 - D) * WIDE_LDT; el += WIDE_WPC * 32) sYt[D + el / WIDE_LDT][el % WIDE_LDT] = 0.0;  // rows past D stay zero
+  double acc[5][2];
+#pragma unroll
+  for (int f = 0; f < 5; f++) acc[f][0] = acc[f][1] = 0.0;
+  const int mA = min(p0 + 2 * warp, M - 1), mB = min(p0 + 2 * warp + 1, M - 1);  // surplus particles shadow the last one
+  const double *kA = Ks + (size_t)mA * ldv, *kB = Ks + (size_t)mB * ldv, *vA = V + (size_t)mA * ldv, *vB = V + (size_t)mB * ldv;
   for (int n0 = seg * WIDE_TILE; n0 < N; n0 += nseg * WIDE_TILE) {
-    __syncthreads();  // previous tile fully consumed (first pass: sX / sXw / sIl visible)
+    __syncthreads();  // previous tile fully consumed (first pass: sXw / sX / sIl and the zero rows visible)
     const int cnt = min(WIDE_TILE, N - n0);
     for (int el = tid; el < WIDE_TILE * D; el += WIDE_WPC * 32) {
       const int i = el / D, j = el - i * D;
-      sY[i][j] = (i < cnt) ? Xtr[(size_t)n0 * D + el] : 0.0;
+      sYt[j][i] = (i < cnt) ? Xtr[(size_t)n0 * D + el] : 0.0;
     }
     if (tid < WIDE_TILE) sA[tid] = (tid < cnt) ? alpha[n0 + tid] : 0.0;
-    __syncthreads();
+    // this warp's share of the weights' inputs: K* and V of its two particles at the tile's points (two points per lane)
+    double kk[2][2], vv[2][2];
 #pragma unroll
-    for (int h = 0; h < WIDE_TILE / 32; h++) {
-      const int i = h * 32 + lane, n = n0 + i;
-      double d2 = 0.0, L1 = off;
-      for (int j = 0; j < D; j++) {
-        const double yj = sY[i][j];
-        const double t = (sX[warp][j] - yj) * sIl[j];
-        d2 = fma(t, t, d2);
-        L1 = fma(sXw[warp][j], yj, L1);
+    for (int h = 0; h < 2; h++) {
+      const int n = n0 + h * 32 + lane;
+      const bool ok = n < N;
+      kk[0][h] = ok ? kA[n] : 0.0;
+      kk[1][h] = ok ? kB[n] : 0.0;
+      vv[0][h] = ok ? vA[n] : 0.0;
+      vv[1][h] = ok ? vB[n] : 0.0;
+    }
+    __syncthreads();
+    if (np1) {  // L1 of all 8 particles at this warp's 16 points: C[p][n] = sum_j xw[p][j] y[n][j]
+#pragma unroll
+      for (int nb = 0; nb < 2; nb++) {
+        const int c0 = (2 * warp + nb) * 8;
+        double l0 = 0.0, l1 = 0.0;
+        for (int k4 = 0; k4 < D; k4 += 4) dmma884(l0, l1, sXw[gq][k4 + q], sYt[k4 + q][c0 + gq]);
+        sL1[gq][c0 + 2 * q] = l0 + off;
+        sL1[gq][c0 + 2 * q + 1] = l1 + off;
       }
-      const double ev = se ? lam * exp(-d2) : 0.0, kv = ev + (np1 ? L1 : 0.0);
-      const double a = sA[i], vn = (n < N) ? v[n] : 0.0;
-      mu = fma(a, kv, mu);
-      q = fma(vn, kv, q);
-      const double ta = a * ev, tv = vn * ev;
-      E0a += ta;
-      E0v += tv;
-      *reinterpret_cast<double4*>(&sT[warp][i][0]) = make_double4(ta, tv, a, vn);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int i = h * 32 + lane;
+      const double a = sA[i];
+#pragma unroll
+      for (int P = 0; P < 2; P++) {
+        const double kv = kk[P][h], vn = vv[P][h];
+        const double ev = se ? (np1 ? kv - sL1[2 * warp + P][i] : kv) : 0.0;
+        sW[warp][4 * P + 0][i] = a * ev;
+        sW[warp][4 * P + 1][i] = vn * ev;
+        sW[warp][4 * P + 2][i] = a;
+        sW[warp][4 * P + 3][i] = vn;
+        sW[warp][8 + P][i] = kv;
+      }
     }
     __syncwarp();
-    if (lane < D) {
-#pragma unroll 8
-      for (int i = 0; i < WIDE_TILE; i++) {
-        const double y = sY[i][lane];
-        const double4 t4 = *reinterpret_cast<const double4*>(&sT[warp][i][0]);
-        acc[0] = fma(y, t4.x, acc[0]);
-        acc[1] = fma(y, t4.y, acc[1]);
-        acc[2] = fma(y, t4.z, acc[2]);
-        acc[3] = fma(y, t4.w, acc[3]);
-      }
+    for (int k4 = 0; k4 < WIDE_TILE; k4 += 4) {
+      const double wa = sW[warp][gq][k4 + q];
+#pragma unroll
+      for (int f = 0; f < 4; f++)
+        if (f < nfy) dmma884(acc[f][0], acc[f][1], wa, sYt[8 * f + gq][k4 + q]);
+      const double sp = gq == 0 ? 1.0 : (gq == 1 ? sW[warp][8][k4 + q] : (gq == 2 ? sW[warp][9][k4 + q] : 0.0));
+      dmma884(acc[4][0], acc[4][1], wa, sp);
+    }
+    __syncwarp();
+  }
+  // result tile of this warp -> shared memory [row][feature] (over its weight rows)
+  double* sG = &sW[warp][0][0];
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    if (f < nfy) {
+      sG[gq * WIDE_LDG + 8 * f + 2 * q] = acc[f][0];
+      sG[gq * WIDE_LDG + 8 * f + 2 * q + 1] = acc[f][1];
     }
   }
-  mu = warp_sum(mu); q = warp_sum(q); E0a = warp_sum(E0a); E0v = warp_sum(E0v);
-  if (lane == 0) { sS[warp][0] = mu; sS[warp][1] = q; sS[warp][2] = E0a; sS[warp][3] = E0v; }
-  if (lane < D) *reinterpret_cast<double4*>(&sG[warp][lane][0]) = make_double4(acc[0], acc[1], acc[2], acc[3]);
+  sG[gq * WIDE_LDG + 8 * nfy + 2 * q] = acc[4][0];
+  sG[gq * WIDE_LDG + 8 * nfy + 2 * q + 1] = acc[4][1];
   if (nseg > 1) {
     cluster.sync();
     if (seg == 0) {  // fixed order: own partial, then ranks 1, 2, 3
+      const int nval = 8 * WIDE_LDG;
       for (int r = 1; r < nseg; r++) {
-        const double* rG = cluster.map_shared_rank(&sG[0][0][0], r);
-        const double* rS = cluster.map_shared_rank(&sS[0][0], r);
-        if (lane < D) {
-#pragma unroll
-          for (int c = 0; c < 4; c++) sG[warp][lane][c] += rG[(warp * MCP_MAX_D + lane) * 4 + c];
-        }
-        if (lane < 4) sS[warp][lane] += rS[warp * 4 + lane];
+        const double* rG = cluster.map_shared_rank(sG, r);
+        for (int i = lane; i < nval; i += 32) sG[i] += rG[i];
       }
     }
     cluster.sync();  // the other ranks' shared memory stays alive until rank 0 has read it
     if (seg != 0) return;
   }
   __syncwarp();
-  E0a = sS[warp][2];
-  E0v = sS[warp][3];
-  if (owner && lane < D) {
-    const int j = lane;
-    const double il2 = -2.0 * sIl[j] * sIl[j], xj = sX[warp][j], w1 = np1 ? s.poly_w2[0][0][j] : 0.0;
-    const double ga = il2 * (xj * E0a - sG[warp][j][0]) + w1 * sG[warp][j][2];
-    const double gv = il2 * (xj * E0v - sG[warp][j][1]) + w1 * sG[warp][j][3];
-    // d k(x,x) / dx_j for SE + linear: 2 w1_j x_j
-    const double dkd = np1 ? 2.0 * w1 * xj : 0.0;
-    jmean[((size_t)m * E + e) * D + j] = ga;
-    jvar[((size_t)m * E + e) * D + j] = var_scale * (dkd - 2.0 * gv);
-  }
-  if (owner && lane == 0) {
-    double kd = se ? lam : 0.0;
-    if (np1) {
-      double L = off;
-      for (int j = 0; j < D; j++) L = fma(s.poly_w2[0][0][j] * sX[warp][j], sX[warp][j], L);
-      kd += L;
+  const int spc = 8 * nfy;  // first column of the special tile
+#pragma unroll
+  for (int P = 0; P < 2; P++) {
+    const int p = 2 * warp + P, m = p0 + p;
+    if (m >= M) continue;
+    const double* G = sG + 4 * P * WIDE_LDG;  // rows: a e, v e, a, v
+    const double E0a = G[0 * WIDE_LDG + spc], E0v = G[1 * WIDE_LDG + spc];
+    if (lane < D) {
+      const int j = lane;
+      const double il2 = -2.0 * sIl[j] * sIl[j], xj = sX[p][j], w1 = np1 ? s.poly_w2[0][0][j] : 0.0;
+      const double ga = il2 * (xj * E0a - G[0 * WIDE_LDG + j]) + w1 * G[2 * WIDE_LDG + j];
+      const double gv = il2 * (xj * E0v - G[1 * WIDE_LDG + j]) + w1 * G[3 * WIDE_LDG + j];
+      const double dkd = np1 ? 2.0 * w1 * xj : 0.0;  // d k(x,x) / dx_j for SE + linear: 2 w1_j x_j
+      jmean[((size_t)m * E + e) * D + j] = ga;
+      jvar[((size_t)m * E + e) * D + j] = var_scale * (dkd - 2.0 * gv);
     }
-    mean[(size_t)m * E + e] = s.mean0 + sS[warp][0];
-    var[(size_t)m * E + e] = var_scale * (kd - sS[warp][1]);
+    if (lane == 0) {
+      double kd = se ? s.lambda : 0.0;
+      if (np1) {
+        double L = off;
+        for (int j = 0; j < D; j++) L = fma(s.poly_w2[0][0][j] * sX[p][j], sX[p][j], L);
+        kd += L;
+      }
+      mean[(size_t)m * E + e] = s.mean0 + G[2 * WIDE_LDG + spc + 1 + P];
+      var[(size_t)m * E + e] = var_scale * (kd - G[3 * WIDE_LDG + spc + 1 + P]);
+    }
   }
 }
 
 __global__ void __launch_bounds__(WIDE_WPC * 32) posterior_reduce_wide_kernel(const __grid_constant__ McpGpSpec s, const double* __restrict__ Xs,
                                                                     int M, const double* __restrict__ Xtr,
-                                                                    const double* __restrict__ alpha, int N,
+                                                                    const double* __restrict__ alpha, int N, const double* __restrict__ Ks,
                                                                     const double* __restrict__ V, int ldv, double var_scale, int E,
                                                                     int e, double* __restrict__ mean, double* __restrict__ var,
                                                                     double* __restrict__ jmean, double* __restrict__ jvar) {
-  reduce_wide_body(s, Xs, M, Xtr, alpha, N, V, ldv, var_scale, E, e, mean, var, jmean, jvar);
+  reduce_wide_body(s, Xs, M, Xtr, alpha, N, Ks, V, ldv, var_scale, E, e, mean, var, jmean, jvar);
 }
 
 // the same reduce for ALL outputs in one launch (blockIdx.y = output); a link of a programmatic-dependent-launch chain
 __global__ void __launch_bounds__(WIDE_WPC * 32) posterior_reduce_wide_batched_kernel(const McpGpDev* __restrict__ gps, const double* __restrict__ Xs,
-                                                                            int M, const double* __restrict__ V, int ldv, size_t gp_stride,
-                                                                            int E, double* __restrict__ mean, double* __restrict__ var,
-                                                                            double* __restrict__ jmean, double* __restrict__ jvar) {
+                                                                            int M, const double* __restrict__ Ks, const double* __restrict__ V,
+                                                                            int ldv, size_t gp_stride, int E, double* __restrict__ mean,
+                                                                            double* __restrict__ var, double* __restrict__ jmean,
+                                                                            double* __restrict__ jvar) {
   pdl_wait();
   const int e = blockIdx.y;
   const McpGpDev& g = gps[e];
-  reduce_wide_body(g.spec, Xs, M, g.Xtr, g.alpha, g.N, V + e * gp_stride, ldv, g.var_scale, E, e, mean, var, jmean, jvar);
+  reduce_wide_body(g.spec, Xs, M, g.Xtr, g.alpha, g.N, Ks + e * gp_stride, V + e * gp_stride, ldv, g.var_scale, E, e, mean, var, jmean, jvar);
 }
 
 // launch with a runtime cluster size along z (and, optionally, programmatic stream serialisation)
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_cluster_z(bool pdl, int nseg, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+static cudaError_t launch_cluster_z(bool pdl, int nseg, size_t smem, void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1083,8 +1132,8 @@ int gp_posterior_batched(const McpGpDev* tab, int E, int D, int nmax, const doub
   MCP_LAUNCH_CHECK();
   if (int err = launch_small_gemm(tab, M, nmax, E, Ks, V, ldk, gp_stride, pdl, st)) return err;
   const int nseg = wide_segments(nmax);  // gp_posterior_batched_ok: every output has this segment count
-  MCP_CUDA(launch_cluster_z(pdl, nseg, posterior_reduce_wide_batched_kernel, dim3(cdiv(M, WIDE_WPC), E, nseg), dim3(WIDE_WPC * 32), st, tab, Xs, M, V, ldk,
-                            gp_stride, E, mean, var, jmean, jvar));
+  MCP_CUDA(launch_cluster_z(pdl, nseg, wide_smem_bytes(D), posterior_reduce_wide_batched_kernel, dim3(cdiv(M, WIDE_PPC), E, nseg), dim3(WIDE_WPC * 32), st, tab, Xs, M, Ks, V,
+                            ldk, gp_stride, E, mean, var, jmean, jvar));
   count_launch();
   return MCP_OK;
 }
@@ -1173,8 +1222,8 @@ int gp_posterior_chunk(const McpGp& g, int E, int e, const double* Xs, int M, do
 #undef MCP_FAST_REDUCE
     } else if (jac && wide_reduce_ok(g.spec)) {
       const int nseg = wide_segments(N);
-      MCP_CUDA(launch_cluster_z(false, nseg, posterior_reduce_wide_kernel, dim3(cdiv(mc, WIDE_WPC), 1, nseg), dim3(WIDE_WPC * 32), st, g.spec, xs, mc, g.Xtr,
-                                g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv));
+      MCP_CUDA(launch_cluster_z(false, nseg, wide_smem_bytes(g.spec.D), posterior_reduce_wide_kernel, dim3(cdiv(mc, WIDE_PPC), 1, nseg), dim3(WIDE_WPC * 32), st, g.spec, xs, mc, g.Xtr,
+                                g.alpha, N, Ks, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E, var + (size_t)m0 * E, jm, jv));
     } else if (jac) {
       MCP_DISPATCH_D(g.spec.D, (posterior_reduce_kernel<DT, true><<<grid, 256, 0, st>>>(
                                    g.spec, xs, mc, g.Xtr, g.alpha, N, V, ldk, g.var_scale, E, e, mean + (size_t)m0 * E,
