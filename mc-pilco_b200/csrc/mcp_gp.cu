@@ -60,17 +60,30 @@ __device__ __forceinline__ void cov_wide_body(const McpGpSpec& s, const double* 
   const int D = s.D, tid = threadIdx.x, nb0 = blockIdx.x * CW_THREADS, n = nb0 + tid, i0 = blockIdx.y * CW_ROWS;
   const bool np1 = s.n_poly == 1;
   const int cnt = min(CW_THREADS, n2 - nb0);
-  for (int el = tid; el < cnt * D; el += CW_THREADS) {
+  for (int el = tid; el < cnt * D; el += CW_THREADS) {  // asynchronous copy: the L2 round trips of the strip overlap instead of queueing
     const int r = el / D, j = el - r * D;
-    sy[r][j] = X2[(size_t)nb0 * D + el];
+    cp_async8(&sy[r][j], X2 + (size_t)nb0 * D + el, 8);
   }
-  for (int el = tid; el < CW_ROWS * DT; el += CW_THREADS) {
-    const int r = el / DT, j = el - r * DT;
-    const double x = (i0 + r < n1 && j < D) ? X1[(size_t)(i0 + r) * D + j] : 0.0;
-    const double w = (np1 && j < D) ? s.poly_w2[0][0][j] : 0.0;
-    sxp[r][j] = make_double2(x, w * x);
+  cp_async_commit();
+  {
+    constexpr int NI = (CW_ROWS * DT + CW_THREADS - 1) / CW_THREADS;
+    double xv[NI];
+#pragma unroll
+    for (int u = 0; u < NI; u++) {  // loads first, stores after
+      const int el = tid + u * CW_THREADS, r = el / DT, j = el - r * DT;
+      xv[u] = (el < CW_ROWS * DT && i0 + r < n1 && j < D) ? X1[(size_t)(i0 + r) * D + j] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < NI; u++) {
+      const int el = tid + u * CW_THREADS, r = el / DT, j = el - r * DT;
+      if (el < CW_ROWS * DT) {
+        const double w = (np1 && j < D) ? s.poly_w2[0][0][j] : 0.0;
+        sxp[r][j] = make_double2(xv[u], w * xv[u]);
+      }
+    }
   }
   if (tid < DT) sil[tid] = tid < D ? s.inv_ls[tid] : 0.0;
+  cp_async_wait<0>();
   __syncthreads();
   if (n >= ncols_out) return;
   double d2[CW_ROWS], a[CW_ROWS];
@@ -910,11 +923,22 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
   const bool se = s.has_se != 0;
   const int nfy = (D + 7) >> 3;       // feature tiles of training inputs; tile nfy is the special one
   const int p0 = blockIdx.x * WIDE_PPC;
-  for (int el = tid; el < WIDE_PPC * WIDE_LDX; el += WIDE_WPC * 32) {
-    const int p = el / WIDE_LDX, j = el - p * WIDE_LDX;
-    const double xj = (j < D && p0 + p < M) ? Xs[(size_t)(p0 + p) * D + j] : 0.0;
-    sXw[p][j] = (np1 && j < D) ? s.poly_w2[0][0][j] * xj : 0.0;
-    if (j < MCP_MAX_D) sX[p][j] = xj;
+  {  // all loads first, then the stores: a store that waits for its load would serialise the L2 round trips (in-order issue)
+    constexpr int NI = (WIDE_PPC * WIDE_LDX + WIDE_WPC * 32 - 1) / (WIDE_WPC * 32);
+    double xv[NI];
+#pragma unroll
+    for (int u = 0; u < NI; u++) {
+      const int el = tid + u * WIDE_WPC * 32, p = el / WIDE_LDX, j = el - p * WIDE_LDX;
+      xv[u] = (el < WIDE_PPC * WIDE_LDX && j < D && p0 + p < M) ? Xs[(size_t)(p0 + p) * D + j] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < NI; u++) {
+      const int el = tid + u * WIDE_WPC * 32, p = el / WIDE_LDX, j = el - p * WIDE_LDX;
+      if (el < WIDE_PPC * WIDE_LDX) {
+        sXw[p][j] = (np1 && j < D) ? s.poly_w2[0][0][j] * xv[u] : 0.0;
+        if (j < MCP_MAX_D) sX[p][j] = xv[u];
+      }
+    }
   }
   if (tid < MCP_MAX_D) sIl[tid] = tid < D ? s.inv_ls[tid] : 0.0;
   for (int el = tid; el < (Dp8 - D) * WIDE_LDT; el += WIDE_WPC * 32) sYt[D + el / WIDE_LDT][el % WIDE_LDT] = 0.0;  // rows past D stay zero
@@ -926,11 +950,12 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
   for (int n0 = seg * WIDE_TILE; n0 < N; n0 += nseg * WIDE_TILE) {
     __syncthreads();  // previous tile fully consumed (first pass: sXw / sX / sIl and the zero rows visible)
     const int cnt = min(WIDE_TILE, N - n0);
-    for (int el = tid; el < WIDE_TILE * D; el += WIDE_WPC * 32) {
+    for (int el = tid; el < WIDE_TILE * D; el += WIDE_WPC * 32) {  // asynchronous, transposing copy: no register round trip
       const int i = el / D, j = el - i * D;
-      sYt[j][i] = (i < cnt) ? Xtr[(size_t)n0 * D + el] : 0.0;
+      cp_async8(&sYt[j][i], Xtr + (i < cnt ? (size_t)n0 * D + el : 0), i < cnt ? 8 : 0);
     }
-    if (tid < WIDE_TILE) sA[tid] = (tid < cnt) ? alpha[n0 + tid] : 0.0;
+    if (tid < WIDE_TILE) cp_async8(&sA[tid], alpha + (tid < cnt ? n0 + tid : 0), tid < cnt ? 8 : 0);
+    cp_async_commit();
     // this warp's share of the weights' inputs: K* and V of its two particles at the tile's points (two points per lane)
     double kk[2][2], vv[2][2];
 #pragma unroll
@@ -942,6 +967,7 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
       vv[0][h] = ok ? vA[n] : 0.0;
       vv[1][h] = ok ? vB[n] : 0.0;
     }
+    cp_async_wait<0>();
     __syncthreads();
     if (np1) {  // L1 of all 8 particles at this warp's 16 points: C[p][n] = sum_j xw[p][j] y[n][j]
 #pragma unroll
@@ -994,10 +1020,14 @@ __device__ __forceinline__ void reduce_wide_body(const McpGpSpec& s, const doubl
   if (nseg > 1) {
     cluster.sync();
     if (seg == 0) {  // fixed order: own partial, then ranks 1, 2, 3
-      const int nval = 8 * WIDE_LDG;
+      constexpr int NV = 8 * WIDE_LDG / 32;  // values per lane
       for (int r = 1; r < nseg; r++) {
         const double* rG = cluster.map_shared_rank(sG, r);
-        for (int i = lane; i < nval; i += 32) sG[i] += rG[i];
+        double t[NV];
+#pragma unroll
+        for (int u = 0; u < NV; u++) t[u] = rG[lane + 32 * u];  // the remote loads in flight together
+#pragma unroll
+        for (int u = 0; u < NV; u++) sG[lane + 32 * u] += t[u];
       }
     }
     cluster.sync();  // the other ranks' shared memory stays alive until rank 0 has read it

@@ -93,14 +93,15 @@ __global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__
   }
 }
 
-// Same policy evaluation for SMALL particle counts (the real MC-PILCO shapes, M = 200..400): one 128-thread block per
-// particle, threads over basis functions, so a few hundred particles still occupy every SM.
-__global__ void __launch_bounds__(128) policy_fwd_block_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
+// Same policy evaluation for SMALL particle counts (the real MC-PILCO shapes, M = 200..400): one block per particle, threads over
+// basis functions (up to 512 threads, so that with the reference's 200 / 400 basis functions every thread has one and the L2 round
+// trips of the centre rows all overlap), so a few hundred particles still occupy every SM.
+__global__ void __launch_bounds__(512) policy_fwd_block_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
                                                                const __grid_constant__ McpNoise nz, int M, int t, int tm,
                                                                const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
                                                                double* __restrict__ u_t, double* __restrict__ Xs) {
-  __shared__ double s_il[MCP_MAX_DP], s_z[MCP_MAX_DP], s_part[4][MCP_MAX_DU], s_u[MCP_MAX_DU];
-  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  __shared__ double s_il[MCP_MAX_DP], s_z[MCP_MAX_DP], s_part[16][MCP_MAX_DU], s_u[MCP_MAX_DU];
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   if (tid < pol.Dp) {
     s_il[tid] = exp(-pol.log_ls[tid]);
     s_z[tid] = policy_feature(pol, pol_in_t + (size_t)m * pol.Ds, t, tid);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(128) policy_fwd_block_kernel(const __grid_cons
   double a[MCP_MAX_DU];
 #pragma unroll
   for (int k = 0; k < MCP_MAX_DU; k++) a[k] = 0.0;
-  for (int b = tid; b < pol.nb; b += 128) {
+  for (int b = tid; b < pol.nb; b += blockDim.x) {
     const double* c = pol.centers + (size_t)b * pol.Dp;
     double d = 0.0;
 #pragma unroll 8
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(128) policy_fwd_block_kernel(const __grid_cons
     }
   __syncthreads();
   if (tid < pol.Du) {
-    double v = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+    double v = 0.0;
+    for (int i = 0; i < nw; i++) v += s_part[i][tid];   // fixed order
     if (pol.has_bias) v += pol.bias[tid];
     if (pol.squash) v = pol.u_max[tid] * tanh(v / pol.u_max[tid]);
     u_t[(size_t)m * pol.Du + tid] = v;
@@ -156,11 +158,16 @@ __global__ void __launch_bounds__(128) policy_fwd_block_kernel(const __grid_cons
   }
 }
 
+static inline int policy_block_threads(int nb) {
+  const int t = (nb + 31) / 32 * 32;
+  return t < 128 ? 128 : (t > 512 ? 512 : t);
+}
+
 // launch the policy evaluation with the mapping that suits the particle count
 static int launch_policy(const McpPolicy& pol, const McpModel& mdl, const McpNoise& nz, int M, int Mg, int t, int tm,
                          const double* pol_in_t, const double* x_t, double* u_t, double* Xs, cudaStream_t st) {
   if (Mg <= 2048)  // chosen from the GLOBAL particle count: shards of one rollout must add the basis functions in the same order
-    policy_fwd_block_kernel<<<M, 128, 0, st>>>(pol, mdl, nz, M, t, tm, pol_in_t, x_t, u_t, Xs);
+    policy_fwd_block_kernel<<<M, policy_block_threads(pol.nb), 0, st>>>(pol, mdl, nz, M, t, tm, pol_in_t, x_t, u_t, Xs);
   else
     policy_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(pol, mdl, nz, M, t, tm, pol_in_t, x_t, u_t, Xs);
   MCP_LAUNCH_CHECK();
