@@ -744,11 +744,16 @@ __global__ void __launch_bounds__(RED_THREADS, 2) posterior_reduce_fast_kernel(c
   const double* vrow = V + (size_t)m * ldv;
   auto stage = [&](int t, int buf) {
     const int n0 = t * RED_TILE;
-    for (int el = tid; el < RED_TILE * D; el += RED_THREADS) {
-      const int i = el / D, j = el - i * D;
-      cp_async8(&sY[buf][j][i], Xtr + (size_t)min(n0 + i, N - 1) * D + j, (n0 + i < N) ? 8 : 0);
+#pragma unroll
+    for (int c = 0; c < RED_TILE / RED_THREADS; c++) {  // thread <-> training point: its D inputs into the D transposed rows, no index division
+      const int i = tid + c * RED_THREADS;
+      const bool ok = n0 + i < N;
+      const double* src = Xtr + (size_t)(ok ? n0 + i : 0) * D;
+#pragma unroll
+      for (int j = 0; j < DT; j++)
+        if (j < D) cp_async8(&sY[buf][j][i], src + j, ok ? 8 : 0);
+      cp_async8(&sA[buf][i], alpha + (ok ? n0 + i : 0), ok ? 8 : 0);
     }
-    for (int i = tid; i < RED_TILE; i += RED_THREADS) cp_async8(&sA[buf][i], alpha + min(n0 + i, N - 1), (n0 + i < N) ? 8 : 0);
 #pragma unroll
     for (int c = 0; c < RED_TILE / 64; c++) {  // rows are 16-byte aligned (ld a multiple of 16 doubles); entries past N arrive as zeros
       const int i = 2 * (lane + 32 * c), left = N - (n0 + i);
