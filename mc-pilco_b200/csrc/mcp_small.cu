@@ -35,6 +35,22 @@ __global__ void gpdev_store_kernel(const __grid_constant__ McpGpDev g, McpGpDev*
 // early-resident successor blocks compete with the running grid — while the implicit form gains 8-12 %.
 
 // ---- batched V_e = K*_e Kinv_e^T (Kinv symmetric), 32 x 32 tiles, 128 threads ----
+// The contraction is short (K = N = 300..400) and there are only a few hundred tiles, so what matters is that the L2 round trip of the
+// operand tiles is covered: k-blocks of 32 in a 3-stage cp.async ring (two blocks = 1000 DMMA-pipe cycles in flight; the generic
+// 16-wide 3-stage ring of mcp_dgemm.cuh keeps ~130 in flight and made this kernel wait for L2 at every k-block: 13.7 us per step at
+// C2 against a 4 us FP64-pipe floor).  Same accumulation order over k as gemm_mainloop: bit-identical results.
+constexpr int SG_BK = 32, SG_LDS = SG_BK + 4, SG_STAGES = 3;   // row stride = 4 (mod 16) doubles: conflict-free fragment loads; 55 KB: four CTAs per SM (the 546 tiles of the UR5 step are one wave)
+constexpr size_t SG_SMEM_BYTES = (size_t)SG_STAGES * 64 * SG_LDS * sizeof(double);
+__device__ __forceinline__ void sg_load_tile(double* __restrict__ s, const double* __restrict__ G, int ld, int r0, int nrows, int k0, int K,
+                                             int tid) {
+#pragma unroll
+  for (int c = tid; c < 32 * (SG_BK / 2); c += 128) {
+    const int row = c / (SG_BK / 2), kc = (c % (SG_BK / 2)) * 2;
+    const int gr = r0 + row, rem = K - (k0 + kc);
+    const int bytes = (gr < nrows && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+    cp_async16(s + row * SG_LDS + kc, bytes ? (G + (size_t)gr * ld + k0 + kc) : G, bytes);
+  }
+}
 __global__ void __launch_bounds__(128) small_gemm_kernel(const McpGpDev* __restrict__ gps, int M, const double* __restrict__ Ks,
                                                          double* __restrict__ V, int ldk, size_t gp_stride) {
   extern __shared__ __align__(16) double smem[];
@@ -48,7 +64,49 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const McpGpDev* __restr
 #pragma unroll
     for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
   const double* A = Ks + blockIdx.z * gp_stride;
-  gemm_mainloop<32, 32, 2, 2>(A, ldk, M, m0, g.Kinv, g.ld, N, n0, 0, N, smem, acc);
+  {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
+    const int wm0 = (warp % 2) * 16, wn0 = (warp / 2) * 16;
+    double* As = smem;
+    double* Bs = smem + SG_STAGES * 32 * SG_LDS;
+    const int KT = (N + SG_BK - 1) / SG_BK;
+#pragma unroll
+    for (int st = 0; st < SG_STAGES - 1; st++) {
+      if (st < KT) {
+        sg_load_tile(As + st * 32 * SG_LDS, A, ldk, m0, M, st * SG_BK, N, tid);
+        sg_load_tile(Bs + st * 32 * SG_LDS, g.Kinv, g.ld, n0, N, st * SG_BK, N, tid);
+      }
+      cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+      cp_async_wait<SG_STAGES - 2>();
+      __syncthreads();
+      {
+        const int nk = kt + SG_STAGES - 1;
+        if (nk < KT) {
+          const int st = nk % SG_STAGES;
+          sg_load_tile(As + st * 32 * SG_LDS, A, ldk, m0, M, nk * SG_BK, N, tid);
+          sg_load_tile(Bs + st * 32 * SG_LDS, g.Kinv, g.ld, n0, N, nk * SG_BK, N, tid);
+        }
+        cp_async_commit();
+      }
+      const double* as = As + (kt % SG_STAGES) * 32 * SG_LDS + (wm0 + gq) * SG_LDS + q;
+      const double* bs = Bs + (kt % SG_STAGES) * 32 * SG_LDS + (wn0 + gq) * SG_LDS + q;
+#pragma unroll
+      for (int ks = 0; ks < SG_BK / 4; ks++) {
+        double a[2], b[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) a[i] = as[i * 8 * SG_LDS + ks * 4];
+#pragma unroll
+        for (int j = 0; j < 2; j++) b[j] = bs[j * 8 * SG_LDS + ks * 4];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    }
+    cp_async_wait<0>();
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm0 = (warp % 2) * 16, wn0 = (warp / 2) * 16, gq = lane >> 2, q = lane & 3;
   double* C = V + blockIdx.z * gp_stride;
@@ -390,8 +448,9 @@ __global__ void __launch_bounds__(SS_THREADS, 3) small_step_kernel(const __grid_
 // host: is this rollout one for the fused small path?
 int launch_small_gemm(const McpGpDev* tab, int M, int nmax, int E, const double* Ks, double* V, int ldk, size_t gp_stride, bool pdl,
                       cudaStream_t st) {
-  MCP_CUDA(launch_chain(pdl, small_gemm_kernel, dim3(cdiv(nmax, 32), cdiv(M, 32), E), dim3(128), gemm_smem_bytes<32, 32>(), st, tab, M, Ks, V, ldk,
-                        gp_stride));
+  static bool cfg[MCP_MAX_DEVICES] = {};
+  MCP_CUDA(ensure_dynamic_smem(cfg, small_gemm_kernel, (int)SG_SMEM_BYTES));
+  MCP_CUDA(launch_chain(pdl, small_gemm_kernel, dim3(cdiv(nmax, 32), cdiv(M, 32), E), dim3(128), SG_SMEM_BYTES, st, tab, M, Ks, V, ldk, gp_stride));
   count_launch();
   return MCP_OK;
 }
