@@ -391,7 +391,19 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double* __restrict__ A
   double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
   double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem + NB * (NB + 1));
   const int tid = threadIdx.x, i = tid >> 2, p = tid & 3;
-  for (int e = tid; e < NB * NB; e += 256) s[e / NB][e % NB] = Akk[(size_t)(e / NB) * lda + (e % NB)];
+  {  // all 16 loads of a thread in flight before the first store (a store waiting on its load would serialise the L2 round trips)
+    double v[NB * NB / 256];
+#pragma unroll
+    for (int u = 0; u < NB * NB / 256; u++) {
+      const int e = tid + u * 256;
+      v[u] = Akk[(size_t)(e / NB) * lda + (e % NB)];
+    }
+#pragma unroll
+    for (int u = 0; u < NB * NB / 256; u++) {
+      const int e = tid + u * 256;
+      s[e / NB][e % NB] = v[u];
+    }
+  }
   __syncthreads();
   __shared__ double rdiag[NB];  // 1 / l_jj: one division per column on the critical path instead of one per row
   for (int j = 0; j < NB; j++) {
