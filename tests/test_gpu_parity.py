@@ -407,11 +407,12 @@ def test_cost_stats_output_and_shard_merge(nh):
     close(std, float(full.cost_out[1]), 1e-10)
 
 
-@pytest.mark.parametrize("N", [40, 96, 200])
+@pytest.mark.parametrize("N", [40, 96, 200, 330])
 def test_ur5_true_dimensions_vs_oracle(nh, N):
     """Config 4 at its real dimensions (D = 24, E = 6, Ds = 12, Du = 6): trajectories, cost and policy gradients against the CPU oracle
     (own precompute on both sides), plus the single-step posterior and its Jacobians.  N = 40: one 64-point tile, no cluster split in the
-    wide reduce; 96: two tiles, clusters of two; 200: four tiles with a ragged tail."""
+    wide reduce; 96: two tiles, clusters of two; 200: four tiles with a ragged tail, clusters of four; 330: six tiles, two of the four CTAs
+    take a second one."""
     from mcpilco_b200 import _ops as ops
     sc = scenarios.ur5_full(N=N)
     ref = Hh.oracle_rollout(sc)
@@ -433,6 +434,35 @@ def test_ur5_true_dimensions_vs_oracle(nh, N):
         gm, = torch.autograd.grad(mu.sum(), xs, retain_graph=True)
         gv, = torch.autograd.grad(var.sum(), xs)
         assert relmax(jm[:, e, :], gm.numpy()) < 1e-6 and relmax(jv[:, e, :], gv.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("D,linear", [(9, True), (13, False), (16, True), (24, False), (31, True), (32, True)])
+def test_wide_posterior_other_widths_vs_oracle(nh, D, linear):
+    """The wide-input posterior (K* kernel, contraction, DMMA reduce over clusters) at input widths other than the UR5's 24 — not a
+    multiple of 4 or 8, the maximum 32 — with and without the linear term, particle counts that leave the last CTA (8 particles)
+    and the last warp (2) ragged: mean, variance and both Jacobians against the oracle and its autograd."""
+    from mcpilco_b200 import _ops as ops, _pack as P
+    rs = np.random.RandomState(100 + D)
+    N, M = 150, 21
+    X = rs.uniform(-1.5, 1.5, (N, D))
+    w = rs.randn(D) / np.sqrt(D)
+    Y = (np.sin(X @ w) + 0.3 * (X @ rs.randn(D)) / np.sqrt(D) + 0.01 * rs.randn(N))[:, None]
+    g = {"D": D, "log_ls": np.log(2.5) + 0.1 * rs.randn(D), "lambda": 1.3, "sigma_n": 0.05, "mean": 0.1,
+         "mpk": [0.1 * np.exp(0.1 * rs.randn(D + 1))] if linear else []}
+    sp = P.spec_from_dict(g)
+    alpha, Kinv = ops.gp_precompute(sp, nh.G(X), nh.G(Y))
+    gp = ops.FittedGp(sp, nh.G(X), alpha, Kinv)
+    Xs = rs.uniform(-1.5, 1.5, (M, D))
+    mu, var, jm, jv = ops.gp_predict([gp], nh.G(Xs), jac=True)
+    # oracle on the same factors
+    sc = {"D": D, "X": X, "Y": Y, "gps": [g]}
+    osp2, oX, oalpha, oKinv = Hh.oracle_fit(sc)[0]
+    xs = Hh.T(Xs).requires_grad_(True)
+    omu, ovar = O.gp_predict(osp2, oX, oalpha, oKinv, xs)
+    gm, = torch.autograd.grad(omu.sum(), xs, retain_graph=True)
+    gv, = torch.autograd.grad(ovar.sum(), xs)
+    assert relmax(mu[:, 0], omu.detach().numpy()) < 1e-8 and relmax(var[:, 0], ovar.detach().numpy()) < 1e-5
+    assert relmax(jm[:, 0, :], gm.numpy()) < 1e-6 and relmax(jv[:, 0, :], gv.numpy()) < 1e-5
 
 
 def test_wide_covariance_kernel_is_bit_identical_to_generic(nh):
