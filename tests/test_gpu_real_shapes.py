@@ -79,6 +79,19 @@ def test_real_shape_rollout_vs_oracle(nh, monkeypatch, key, path):
     check(nh, sc, oracle_of(key, sc), "%s/%s" % (key, path))
 
 
+@pytest.mark.parametrize("nb", [7, 32, 33, 224, 225, 512])
+@pytest.mark.parametrize("key", ["c1", "c3"])
+def test_backward_sweep_basis_function_counts_vs_oracle(nh, monkeypatch, key, nb):
+    """The backward sweep puts one thread per basis function plus one chain warp: basis-function counts below / at / above a warp, at
+    the 256-thread variant's limit (224 + 32), just above it and at the maximum (16 basis warps + the chain warp), with and without
+    the measurement model.  Cart-pole shape with few particles; forward + backward against the oracle."""
+    from mcpilco_b200 import workloads as W
+    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_BATCHED_STEP", "MCPILCO_NO_PDL", "MCPILCO_NO_PERSIST", "MCPILCO_PERSIST"):
+        monkeypatch.delenv(v, raising=False)
+    sc = W.real_shape(key, N=64, M=37, H=9, nb=nb)
+    check(nh, sc, oracle_of("bwd-%s-%d" % (key, nb), sc), "%s/nb=%d" % (key, nb))
+
+
 def test_sweep_midsize_bench_kernels_vs_oracle(nh):
     """C5 at N = 2048, M = 4096, H = 4 with the bench's policy (nb = 200): more than 2048 particles, so this is the per-step path the
     bench times — cov_fast, the TMA-pipelined DMMA contraction over several 128-row tiles, the fast reduce, the 7-warp backward."""
