@@ -92,6 +92,18 @@ def test_backward_sweep_basis_function_counts_vs_oracle(nh, monkeypatch, key, nb
     check(nh, sc, oracle_of("bwd-%s-%d" % (key, nb), sc), "%s/nb=%d" % (key, nb))
 
 
+@pytest.mark.parametrize("key,M", [("c1", 1000), ("c3", 433), ("c2", 2048)])
+def test_cluster_kernel_several_batches_per_cluster_vs_oracle(nh, monkeypatch, key, M):
+    """More particles than the 15 co-resident clusters x 27 take in one pass: every cluster walks several batches (state reset, the
+    K^-1 slice ring carried across batches), the last batch ragged; 2048 is the path's upper limit."""
+    from mcpilco_b200 import workloads as W
+    for v in ("MCPILCO_NO_SMALL_PATH", "MCPILCO_NO_BATCHED_STEP", "MCPILCO_NO_PDL", "MCPILCO_NO_PERSIST"):
+        monkeypatch.delenv(v, raising=False)
+    monkeypatch.setenv("MCPILCO_PERSIST", "1")
+    sc = W.real_shape(key, N=90, M=M, H=5)
+    check(nh, sc, oracle_of("batches-%s-%d" % (key, M), sc), "%s/M=%d" % (key, M))
+
+
 def test_sweep_midsize_bench_kernels_vs_oracle(nh):
     """C5 at N = 2048, M = 4096, H = 4 with the bench's policy (nb = 200): more than 2048 particles, so this is the per-step path the
     bench times — cov_fast, the TMA-pipelined DMMA contraction over several 128-row tiles, the fast reduce, the 7-warp backward."""
