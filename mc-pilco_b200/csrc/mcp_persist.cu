@@ -27,6 +27,10 @@
 // get_estimate_from_alpha (gpr_lib/GP_prior/GP_prior.py:137-155), Sum_of_gaussians.forward (Policy.py:242-265).
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "mcp_gpdev.cuh"
 #include "mcp_kfn.cuh"
 #include "mcp_rollout_dev.cuh"
@@ -612,6 +616,40 @@ persist_rollout_kernel(const __grid_constant__ McpRollout r, const McpGpDev* __r
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------------
+// co-resident clusters of this kernel at a given shared-memory size (asked of the driver once per device and size; all template
+// instances use the same registers and shared memory).  scripts/probe/cluster_occ.cu: 15 above 113 KB with this register count.
+static int pk_max_clusters(size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, size_t>, int> cache;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 15;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({dev, smem});
+  if (it != cache.end()) return it->second;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int n = 15 * sms / 148;
+  static bool cfg_[MCP_MAX_DEVICES] = {};
+  if (ensure_dynamic_smem(cfg_, persist_rollout_kernel<6, 0, true>, 227 * 1024) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PK_CL * 64);
+    cfg.blockDim = dim3(PK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = PK_CL;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, persist_rollout_kernel<6, 0, true>, &cfg) == cudaSuccess && q >= 1) n = q;
+    else (void)cudaGetLastError();
+  }
+  if (n < 1) n = 1;
+  cache[{dev, smem}] = n;
+  return n;
+}
+
 bool persist_path_ok(const McpRollout* r) {
   const char* off = getenv("MCPILCO_NO_PERSIST");
   if (off != nullptr && off[0] == '1') return false;
@@ -633,12 +671,17 @@ bool persist_path_ok(const McpRollout* r) {
     if (r->gps[e].N != r->gps[0].N) return false;  // one zero padding of the slice buffer serves every output
     nmax = r->gps[e].N > nmax ? r->gps[e].N : nmax;
   }
-  if (pk_geom(nmax, r->model.E).doubles * sizeof(double) > 227 * 1024) return false;
+  const size_t smem = pk_geom(nmax, r->model.E).doubles * sizeof(double);
+  if (smem > 227 * 1024) return false;
   // Eligible.  Measured on B200 against the fused two-launch-per-step path (profiles/r02_real_shape_paths.txt): with Volterra terms
   // in the kernel (C1) this path is faster at every N that fits; with SE-only outputs (C2, C3) it is faster up to N ~ 250 and a few
   // per cent slower at N = 300, where the per-step DMMA work outgrows the launch latency it saves.  MCPILCO_PERSIST=1 forces it.
   const char* force = getenv("MCPILCO_PERSIST");
   if (force != nullptr && force[0] == '1') return true;
+  // ... and only while one pass covers the rollout: a cluster that has to walk several particle batches one after the other loses to
+  // the per-step path, which spreads all particles over the GPU at every step (scripts/path_vs_particles.py: 0.88-0.94 of the fused
+  // path's time at 400 particles, 1.0-1.2 at 800, 1.3-1.8 at 2048)
+  if (cdiv(Mg, PK_P) > pk_max_clusters(smem)) return false;  // the GLOBAL count: shards must take the unsharded rollout's path
   return np >= 1 || nmax <= 240;
 }
 
@@ -653,11 +696,7 @@ int rollout_fwd_persist(const McpRollout* r, const double* nv0, double* scratch,
   MCP_CUDA(gpdev_upload(tab, r->gps, E, st));
   const PkGeom G = pk_geom(nmax, E);
   const size_t smem = G.doubles * sizeof(double);
-  int dev = 0, sms = 148;
-  MCP_CUDA(cudaGetDevice(&dev));
-  MCP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int clusters = 15 * sms / 148;  // co-resident clusters of 8 CTAs at this shared-memory size (scripts/probe/cluster_occ.cu); more would only queue
-  if (clusters < 1) clusters = 1;
+  int clusters = pk_max_clusters(smem);  // co-resident clusters of 8 CTAs at this shared-memory size; more would only queue
   const int batches = cdiv(M, PK_P);
   if (clusters > batches) clusters = batches;
   const int np = r->gps[0].spec.n_poly;
