@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(256) cov_kernel(const __grid_constant__ McpGpS
 
 // K* tiles for WIDE gp inputs (8 < D <= 32: SE + at most one linear term, the UR5 model).  The generic kernel keeps x[DT], y[DT] in
 // registers and walks the whole McpGpSpec per entry (~100 loads); here one thread owns a training point (column), the block a strip of
-// 16 particles: the training tile is staged coalesced, the particle rows as (x, w1 x) pairs read by broadcast, and the loop runs
-// dimension-outer over 16 row accumulators.  Arithmetic per entry is exactly KFn::k's, so the result is bit-identical to cov_kernel.
-constexpr int CW_THREADS = 128, CW_ROWS = 16;
+// 8 particles (16 measured 2 us per UR5 step slower: too few CTAs): the training tile is staged coalesced, the particle rows as (x, w1 x) pairs read by broadcast, and the loop runs
+// dimension-outer over the row accumulators.  Arithmetic per entry is exactly KFn::k's, so the result is bit-identical to cov_kernel.
+constexpr int CW_THREADS = 128, CW_ROWS = 8;
 static bool wide_reduce_ok(const McpGpSpec& s);
 template <int DT>
 __device__ __forceinline__ void cov_wide_body(const McpGpSpec& s, const double* __restrict__ X1, int n1, const double* __restrict__ X2, int n2,
