@@ -75,7 +75,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_m = (M + T_BM - 1) / T_BM, tiles_n = (N + T_BN - 1) / T_BN;
   const int per_group = T_GROUP * tiles_n, group = blockIdx.x / per_group, first_m = group * T_GROUP;
   const int rows_here = min(tiles_m - first_m, T_GROUP), in_group = blockIdx.x - group * per_group;
-  const int m0 = (first_m + in_group % rows_here) * T_BM;
+  int mt = first_m + in_group % rows_here;
+  // contraction trimmed to k < m0 + tile (A lower triangular): the heavy row blocks are the last ones, schedule them first
+  if (TRIM && (kflags & KF_A_LOWER) && !(kflags & (KF_A_UPPER | KF_B_UPPER | KF_B_LOWER))) mt = tiles_m - 1 - mt;
+  const int m0 = mt * T_BM;
   int nt = in_group / rows_here;
   // contraction trimmed to k < n0 + tile (B lower triangular): the work of a tile grows with its column index, so the heavy
   // columns are scheduled first and the short ones fill the tail of the last wave
