@@ -382,8 +382,8 @@ constexpr int NB = 64;
 
 // Factor one 64x64 diagonal block in place (lower), write inv(L_kk) (lower, dense 64x64) to `invL` and its transpose to `invLt`
 // (both with leading dimension ldi).  Non-SPD input yields NaN (sqrt of a negative pivot) which propagates, like every
-// numerical failure here.  Four threads per row (left-looking Cholesky: the dot product of a column step is split four ways
-// and combined by shuffles) and four threads per column of the inverse (forward substitution), everything in shared memory.
+// numerical failure here.  Panel-blocked Cholesky (see below) and four threads per column of the inverse (forward substitution),
+// everything in shared memory.
 constexpr int POTRF_SMEM = 2 * NB * (NB + 1) * (int)sizeof(double);
 __global__ void __launch_bounds__(256) potrf_block_kernel(double* __restrict__ Akk, int lda, double* __restrict__ invL,
                                                           double* __restrict__ invLt, int ldi) {
@@ -405,45 +405,105 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double* __restrict__ A
     }
   }
   __syncthreads();
-  __shared__ double rdiag[NB];  // 1 / l_jj: one division per column on the critical path instead of one per row
-  for (int j = 0; j < NB; j++) {
-    // row i, column j:  a_ij - sum_{k<j} l_ik l_jk   (rows above the diagonal idle); two independent chains per thread
-    double d0 = 0.0, d1 = 0.0;
-    if (i >= j) {
-      int k = p;
-      for (; k + 4 < j; k += 8) { d0 = fma(s[i][k], s[j][k], d0); d1 = fma(s[i][k + 4], s[j][k + 4], d1); }
-      if (k < j) d0 = fma(s[i][k], s[j][k], d0);
-    }
-    double dot = d0 + d1;
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    if (i == j && p == 0) {
-      const double d = sqrt(s[j][j] - dot);
-      s[j][j] = d;
-      rdiag[j] = 1.0 / d;
+  __shared__ double rdiag[NB];  // 1 / l_jj
+  // Cholesky in panels of 16 columns: warp 0 factors the 16 x 16 diagonal block warp-synchronously (two lanes per row, no block
+  // barrier), one thread per row solves the panel below it, all threads apply the rank-16 update to the trailing lower triangle.
+  // 3 block barriers per panel (12 in all) instead of 2 per column (128): the leaf was barrier- and latency-bound.
+  constexpr int PW = 16;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int c0 = 0; c0 < NB; c0 += PW) {
+    if (warp == 0) {
+      // the 16 x 16 diagonal block in registers, lane r (and its mirror r + 16) holding row r; right-looking: per column one pivot
+      // broadcast, then 15 - j independent shuffle + FMA pairs — no shared-memory round trip on the column-to-column chain
+      const int r = lane & (PW - 1);
+      double a[PW];
+#pragma unroll
+      for (int k = 0; k < PW; k++) a[k] = s[c0 + r][c0 + k];
+#pragma unroll
+      for (int j = 0; j < PW; j++) {
+        const double piv = sqrt(__shfl_sync(0xffffffffu, a[j], j));  // NaN for a non-positive pivot, which propagates
+        const double rp = 1.0 / piv;
+        const double lrj = (r == j) ? piv : a[j] * rp;
+        a[j] = lrj;
+        if (lane == j) rdiag[c0 + j] = rp;
+#pragma unroll
+        for (int k = j + 1; k < PW; k++) a[k] = fma(-lrj, __shfl_sync(0xffffffffu, lrj, k), a[k]);  // meaningful for r >= k
+      }
+      if (lane < PW) {
+#pragma unroll
+        for (int k = 0; k < PW; k++)
+          if (k <= r) s[c0 + r][c0 + k] = a[k];
+      }
     }
     __syncthreads();
-    if (i > j && p == 0) s[i][j] = (s[i][j] - dot) * rdiag[j];
+    const int R = c0 + PW, nrows = NB - R;
+    if (tid < nrows) {  // row R + tid of the panel:  l_rj = (a_rj - sum_{k<j} l_rk l_jk) / l_jj
+      const int r = R + tid;
+      double l[PW];
+#pragma unroll
+      for (int j = 0; j < PW; j++) {
+        double a = s[r][c0 + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) a = fma(-l[k], s[c0 + j][c0 + k], a);
+        l[j] = a * rdiag[c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < PW; j++) s[r][c0 + j] = l[j];
+    }
+    __syncthreads();
+    for (int ii = tid >> 4; ii < nrows; ii += 16) {  // trailing lower triangle:  a_ik -= sum_j l_ij l_kj
+      for (int kk = tid & 15; kk <= ii; kk += 16) {
+        double a = s[R + ii][R + kk];
+#pragma unroll
+        for (int j = 0; j < PW; j++) a = fma(-s[R + ii][c0 + j], s[R + kk][c0 + j], a);
+        s[R + ii][R + kk] = a;
+      }
+    }
     __syncthreads();
   }
   for (int e = tid; e < NB * NB; e += 256) {
     int r = e / NB, k = e % NB;
     Akk[(size_t)r * lda + k] = (k <= r) ? s[r][k] : 0.0;
   }
-  // inverse: column c = i of X = L^-1 by forward substitution,  x_rc = (delta_rc - sum_{c<=k<r} l_rk x_kc) / l_rr
-  {
-    const int c = i;
-    for (int r = 0; r < NB; r++) {
-      double a0 = 0.0, a1 = 0.0;
-      int k = c + p;
-      for (; k + 4 < r; k += 8) { a0 = fma(s[r][k], x[k][c], a0); a1 = fma(s[r][k + 4], x[k + 4][c], a1); }
-      if (k < r) a0 = fma(s[r][k], x[k][c], a0);
-      double acc = a0 + a1;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (p == 0) x[r][c] = (r < c) ? 0.0 : ((r == c ? 1.0 : 0.0) - acc) * rdiag[r];
-      __syncwarp();
+  // inverse X = L^-1 in 16 x 16 blocks.  Diagonal blocks first, all four at once (warp b, lane c: column c of X_bb by forward
+  // substitution in registers, x_r = (delta_rc - sum_{c<=k<r} l_rk x_k) / l_rr; the l_rk are broadcast reads).  Then block row by block
+  // row  X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj): two small products with all threads, no serial chain inside.
+  for (int e = tid; e < NB * (NB + 1); e += 256) (&x[0][0])[e] = 0.0;
+  __syncthreads();
+  if (warp < NB / PW && lane < PW) {
+    const int b0 = warp * PW, c = lane;
+    double xc[PW];
+#pragma unroll
+    for (int r = 0; r < PW; r++) {
+      double acc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; k++) acc = fma(-s[b0 + r][b0 + k], (k >= c) ? xc[k] : 0.0, acc);
+      xc[r] = (r < c) ? 0.0 : acc * rdiag[b0 + r];
     }
+#pragma unroll
+    for (int r = 0; r < PW; r++) x[b0 + r][b0 + c] = xc[r];
+  }
+  __syncthreads();
+  double (*tmp)[NB + 1] = s;  // T_ij goes where the (already exported) strict upper triangle of s is: rows j-block, cols i-block — see below
+  for (int bi = 1; bi < NB / PW; bi++) {
+    const int i0 = bi * PW;
+    // T[r][c] = sum_{k = j0}^{i0 - 1} L[i0 + r][k] X[k][c]   for every column c < i0 (its block column j0 = c / 16 * 16); X[k][c] = 0 for k < c
+    for (int e = tid; e < PW * i0; e += 256) {
+      const int r = e / i0, c = e - r * i0;
+      double acc = 0.0;
+      for (int k = c; k < i0; k++) acc = fma(s[i0 + r][k], x[k][c], acc);
+      tmp[c][i0 + r] = acc;  // stored transposed into the upper triangle of s (c < i0 <= i0 + r): free space, no clash with L
+    }
+    __syncthreads();
+    // X[i0 + r][c] = -sum_{q <= r} X_ii[r][q] T[q][c]
+    for (int e = tid; e < PW * i0; e += 256) {
+      const int r = e / i0, c = e - r * i0;
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < PW; q++) acc = fma(x[i0 + r][i0 + q], (q <= r) ? tmp[c][i0 + q] : 0.0, acc);
+      x[i0 + r][c] = -acc;
+    }
+    __syncthreads();
   }
   __syncthreads();
   for (int e = tid; e < NB * NB; e += 256) {
