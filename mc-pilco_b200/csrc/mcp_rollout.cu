@@ -443,9 +443,21 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
   __shared__ int s_active;
 
   if (tid < Dp) s_il[tid] = exp(-pol.log_ls[tid]);
-  double cb[DPT], gc[DPT], wb[DUT], gw[DUT];
+  // centres of this thread's basis function: registers, or — widest instance (up to 32 features: centres + their gradient accumulators
+  // + the per-step terms would be 96 doubles per thread and spilled) — a [feature][thread] array in shared memory behind the ring
+  constexpr bool CB_SMEM = DPT > 16;
+  constexpr int CBR = CB_SMEM ? 1 : DPT;
+  double cb_reg[CBR], gc[DPT], wb[DUT], gw[DUT];
+  double* const s_cb = bw_ring + (size_t)BW_RING * slot_n;  // [Dp][blockDim.x] (CB_SMEM only)
+#define MCP_CBV(j) (CB_SMEM ? s_cb[(size_t)(j) * nthr + tid] : cb_reg[CB_SMEM ? 0 : (j)])
+  const int nthr = blockDim.x;
 #pragma unroll
-  for (int j = 0; j < DPT; j++) { cb[j] = (has_b && j < Dp) ? pol.centers[(size_t)b * Dp + j] : 0.0; gc[j] = 0.0; }
+  for (int j = 0; j < DPT; j++) {
+    const double c = (has_b && j < Dp) ? pol.centers[(size_t)b * Dp + j] : 0.0;
+    if (CB_SMEM) { if (j < Dp) s_cb[(size_t)j * nthr + tid] = c; }
+    else cb_reg[CB_SMEM ? 0 : j] = c;
+    gc[j] = 0.0;
+  }
 #pragma unroll
   for (int k = 0; k < DUT; k++) { wb[k] = (has_b && k < Du) ? pol.W[(size_t)k * nb + b] : 0.0; gw[k] = 0.0; }
   const bool drop = dropout_active(pol, r.noise);
@@ -539,7 +551,7 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
         double d = 0.0;
 #pragma unroll
         for (int j = 0; j < DPT; j++)
-          if (j < Dp) { double q = (z[j] - cb[j]) * s_il[j]; d = fma(q, q, d); }
+          if (j < Dp) { double q = (z[j] - MCP_CBV(j)) * s_il[j]; d = fma(q, q, d); }
         h = exp(-d);
         if (drop) h = keep_unit(r.noise, M, nb, tt, tt, m, b) ? h * keep_scale : 0.0;
       }
@@ -624,15 +636,20 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
         for (int k = 0; k < DUT; k++)
           if (k < Du) { gw[k] = fma(s_la[k], h, gw[k]); lh = fma(s_la[k], wb[k], lh); }
         const double ld_b = -h * lh;
-        double cz[DPT];
+        constexpr int CH = DPT > 16 ? 16 : DPT;  // features per butterfly (the widest instance takes two, to stay in registers)
+        constexpr int SH = CH == 8 ? 2 : 1;
 #pragma unroll
-        for (int j = 0; j < DPT; j++) {
-          cz[j] = (j < Dp) ? ld_b * 2.0 * (z[j] - cb[j]) * s_il[j] * s_il[j] : 0.0;  // d/dz_j ; d/dc_bj = -cz
-          gc[j] -= cz[j];
+        for (int j0 = 0; j0 < DPT; j0 += CH) {
+          double cz[CH];
+#pragma unroll
+          for (int jj = 0; jj < CH; jj++) {
+            const int j = j0 + jj;
+            cz[jj] = (j < Dp) ? ld_b * 2.0 * (z[j] - MCP_CBV(j)) * s_il[j] * s_il[j] : 0.0;  // d/dz_j ; d/dc_bj = -cz
+            gc[j] -= cz[jj];
+          }
+          warp_sum_multi<CH>(cz, lane);
+          if ((lane & ((1 << SH) - 1)) == 0 && j0 + (lane >> SH) < Dp) s_red[warp][j0 + (lane >> SH)] = cz[0];
         }
-        warp_sum_multi<DPT>(cz, lane);
-        constexpr int SH = DPT == 8 ? 2 : (DPT == 16 ? 1 : 0);
-        if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < Dp) s_red[warp][lane >> SH] = cz[0];
       }
       __syncthreads();  // Z
       if (chain) {
@@ -698,12 +715,16 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
   //   g_logls_j = sum_steps sum_b [d/dc_bj contribution] (z_j - c_bj) = -sum_steps z_j lz_j - sum_b c_bj g_c[b][j]
   double* P = partials + (size_t)blockIdx.x * (Dp + (size_t)nb * Dp + (size_t)Du * nb + Du);
   if (!chain) {
-    double cg[DPT];
+    constexpr int CH = DPT > 16 ? 16 : DPT;
+    constexpr int SH = CH == 8 ? 2 : 1;
 #pragma unroll
-    for (int j = 0; j < DPT; j++) cg[j] = cb[j] * gc[j];
-    warp_sum_multi<DPT>(cg, lane);
-    constexpr int SH = DPT == 8 ? 2 : (DPT == 16 ? 1 : 0);
-    if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < Dp) s_red[warp][lane >> SH] = cg[0];
+    for (int j0 = 0; j0 < DPT; j0 += CH) {
+      double cg[CH];
+#pragma unroll
+      for (int jj = 0; jj < CH; jj++) cg[jj] = (j0 + jj < Dp) ? MCP_CBV(j0 + jj) * gc[j0 + jj] : 0.0;
+      warp_sum_multi<CH>(cg, lane);
+      if ((lane & ((1 << SH) - 1)) == 0 && j0 + (lane >> SH) < Dp) s_red[warp][j0 + (lane >> SH)] = cg[0];
+    }
   }
   __syncthreads();
   if (chain) {
@@ -723,6 +744,8 @@ __global__ void __launch_bounds__(NT, NCTA) rollout_bwd_kernel(const __grid_cons
       if (k < Du) P[Dp + (size_t)nb * Dp + (size_t)k * nb + b] = gw[k];
   }
 }
+
+#undef MCP_CBV
 
 // out[i] = sum over CTAs of partials[cta][i] (fixed order -> bit-stable)
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int ncta, int n, double* __restrict__ out) {
@@ -969,16 +992,24 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_bwd(const 
   const int nparam = Dp + nb * Dp + Du * nb + Du;
   const int threads = (nb + 31) / 32 * 32 + 32;  // one thread per basis function + the chain warp
   const size_t ring = (size_t)BW_RING * (3 * r->model.Ds + 2 * Du + r->model.E * r->model.D) * sizeof(double);  // <= 37 KB
+  const size_t smem_cb = Dp > 16 ? (size_t)Dp * threads * sizeof(double) : 0;   // the widest instance keeps the centres in shared memory
   // up to 224 basis functions: 256 threads and three resident CTAs per SM (the reference's 400 particles are one wave); else 544 threads
-#define MCP_BWD(DPT, DUT)                                                                                          \
-  do {                                                                                                             \
-    if (threads <= 256) rollout_bwd_kernel<DPT, DUT, 256, 3><<<w.bwd_ctas, threads, ring, st>>>(*r, *g, w.partials, g->g_x0); \
-    else rollout_bwd_kernel<DPT, DUT, 544, 1><<<w.bwd_ctas, threads, ring, st>>>(*r, *g, w.partials, g->g_x0);    \
+#define MCP_BWD_ONE(DPT, DUT, NT, NC)                                                                             \
+  do {                                                                                                            \
+    static bool cfg_[MCP_MAX_DEVICES] = {};                                                                       \
+    MCP_CUDA(ensure_dynamic_smem(cfg_, rollout_bwd_kernel<DPT, DUT, NT, NC>, 200 * 1024));                        \
+    rollout_bwd_kernel<DPT, DUT, NT, NC><<<w.bwd_ctas, threads, ring + smem_cb, st>>>(*r, *g, w.partials, g->g_x0); \
+  } while (0)
+#define MCP_BWD(DPT, DUT)                                       \
+  do {                                                          \
+    if (threads <= 256) MCP_BWD_ONE(DPT, DUT, 256, 3);          \
+    else MCP_BWD_ONE(DPT, DUT, 544, 1);                         \
   } while (0)
   if (Dp <= 8) { if (Du <= 2) MCP_BWD(8, 2); else MCP_BWD(8, 8); }
   else if (Dp <= 16) { if (Du <= 2) MCP_BWD(16, 2); else MCP_BWD(16, 8); }
   else { if (Du <= 2) MCP_BWD(32, 2); else MCP_BWD(32, 8); }
 #undef MCP_BWD
+#undef MCP_BWD_ONE
   MCP_LAUNCH_CHECK();
   reduce_partials_kernel<<<cdiv(nparam, 128), 128, 0, st>>>(w.partials, w.bwd_ctas, nparam, w.flat);
   MCP_LAUNCH_CHECK();
