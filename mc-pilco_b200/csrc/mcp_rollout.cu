@@ -96,10 +96,9 @@ __global__ void __launch_bounds__(256) policy_fwd_kernel(const __grid_constant__
 // Same policy evaluation for SMALL particle counts (the real MC-PILCO shapes, M = 200..400): one block per particle, threads over
 // basis functions (up to 512 threads, so that with the reference's 200 / 400 basis functions every thread has one and the L2 round
 // trips of the centre rows all overlap), so a few hundred particles still occupy every SM.
-__global__ void __launch_bounds__(512) policy_fwd_block_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
-                                                               const __grid_constant__ McpNoise nz, int M, int t, int tm,
-                                                               const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
-                                                               double* __restrict__ u_t, double* __restrict__ Xs) {
+__device__ __forceinline__ void policy_block_body(const McpPolicy& pol, const McpModel& mdl, const McpNoise& nz, int M, int t, int tm,
+                                                  const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
+                                                  double* __restrict__ u_t, double* __restrict__ Xs) {
   __shared__ double s_il[MCP_MAX_DP], s_z[MCP_MAX_DP], s_part[16][MCP_MAX_DU], s_u[MCP_MAX_DU];
   const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   if (tid < pol.Dp) {
@@ -156,6 +155,13 @@ __global__ void __launch_bounds__(512) policy_fwd_block_kernel(const __grid_cons
     }
     Xs[(size_t)m * mdl.D + j] = f;
   }
+}
+
+__global__ void __launch_bounds__(512) policy_fwd_block_kernel(const __grid_constant__ McpPolicy pol, const __grid_constant__ McpModel mdl,
+                                                               const __grid_constant__ McpNoise nz, int M, int t, int tm,
+                                                               const double* __restrict__ pol_in_t, const double* __restrict__ x_t,
+                                                               double* __restrict__ u_t, double* __restrict__ Xs) {
+  policy_block_body(pol, mdl, nz, M, t, tm, pol_in_t, x_t, u_t, Xs);
 }
 
 static inline int policy_block_threads(int nb) {
@@ -259,15 +265,12 @@ __global__ void init_particles_kernel(int kind, const double* __restrict__ a, co
 
 // The same step with one WARP per particle (lanes over outputs, then over the E x D checkpoint entries): used for small particle
 // counts, where a thread per particle leaves the GPU idle behind a serial E x D loop.
-__global__ void __launch_bounds__(256) integrate_warp_kernel(const __grid_constant__ McpModel mdl, const __grid_constant__ McpMeas ms,
-                                                             const __grid_constant__ McpNoise nz, int M, int t,
-                                                             const double* __restrict__ x_t, const double* __restrict__ mean,
-                                                             const double* __restrict__ var, const double* __restrict__ jmean,
-                                                             const double* __restrict__ jvar, double* __restrict__ x_n,
-                                                             double* __restrict__ jac_t, const double* __restrict__ polin_t,
-                                                             double* __restrict__ polin_n, double* __restrict__ nv) {
-  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (m >= M) return;
+__device__ __forceinline__ void integrate_warp_body(const McpModel& mdl, const McpMeas& ms, const McpNoise& nz, int M, int t, int m, int lane,
+                                                    const double* __restrict__ x_t, const double* __restrict__ mean,
+                                                    const double* __restrict__ var, const double* __restrict__ jmean,
+                                                    const double* __restrict__ jvar, double* __restrict__ x_n,
+                                                    double* __restrict__ jac_t, const double* __restrict__ polin_t,
+                                                    double* __restrict__ polin_n, double* __restrict__ nv) {
   const int E = mdl.E, D = mdl.D, Ds = mdl.Ds;
   const double* x = x_t + (size_t)m * Ds;
   double* xn = x_n + (size_t)m * Ds;
@@ -322,6 +325,34 @@ __global__ void __launch_bounds__(256) integrate_warp_kernel(const __grid_consta
       pn[iv] = mv_new;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) integrate_warp_kernel(const __grid_constant__ McpModel mdl, const __grid_constant__ McpMeas ms,
+                                                             const __grid_constant__ McpNoise nz, int M, int t,
+                                                             const double* __restrict__ x_t, const double* __restrict__ mean,
+                                                             const double* __restrict__ var, const double* __restrict__ jmean,
+                                                             const double* __restrict__ jvar, double* __restrict__ x_n,
+                                                             double* __restrict__ jac_t, const double* __restrict__ polin_t,
+                                                             double* __restrict__ polin_n, double* __restrict__ nv) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  integrate_warp_body(mdl, ms, nz, M, t, m, lane, x_t, mean, var, jmean, jvar, x_n, jac_t, polin_t, polin_n, nv);
+}
+
+// Small particle counts: the model step t -> t+1 and the policy evaluation at t+1 of one particle in ONE block (warp 0 integrates, a
+// block barrier, then all threads evaluate the policy): one launch boundary less on the per-step chain.
+__global__ void __launch_bounds__(512) integrate_policy_block_kernel(const __grid_constant__ McpModel mdl, const __grid_constant__ McpMeas ms,
+                                                                     const __grid_constant__ McpNoise nz, const __grid_constant__ McpPolicy pol,
+                                                                     int M, int t, const double* __restrict__ x_t,
+                                                                     const double* __restrict__ mean, const double* __restrict__ var,
+                                                                     const double* __restrict__ jmean, const double* __restrict__ jvar,
+                                                                     double* __restrict__ x_n, double* __restrict__ jac_t,
+                                                                     const double* __restrict__ polin_t, double* __restrict__ polin_n,
+                                                                     double* __restrict__ nv, double* __restrict__ u_n, double* __restrict__ Xs) {
+  if (threadIdx.x < 32)
+    integrate_warp_body(mdl, ms, nz, M, t, (int)blockIdx.x, (int)threadIdx.x, x_t, mean, var, jmean, jvar, x_n, jac_t, polin_t, polin_n, nv);
+  __syncthreads();  // the block's own global writes (x_{t+1}, the policy input) are visible to it after the barrier
+  policy_block_body(pol, mdl, nz, M, t + 1, t + 1, ms.enabled ? polin_n : x_n, x_n, u_n, Xs);
 }
 
 __global__ void init_nv_kernel(const __grid_constant__ McpMeas ms, int M, int Ds, const double* __restrict__ x0, double* __restrict__ nv) {
@@ -926,9 +957,12 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
   for (int t = 0; t < H && !small; t++) {
     const double* x_t = r->states + (size_t)t * M * Ds;
     const double* p_t = meas ? r->pol_in + (size_t)t * M * Ds : x_t;
-    if (int err = launch_policy(r->policy, r->model, r->noise, M, Mg, t, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
-                                t < H - 1 ? w.Xs : nullptr, st))
-      return err;
+    const bool fused_tail = Mg <= 2048;  // block-per-particle policy: evaluated by the kernel that made x_t (below), except at t = 0
+    if (t == 0 || !fused_tail) {
+      if (int err = launch_policy(r->policy, r->model, r->noise, M, Mg, t, t, p_t, x_t, r->inputs + (size_t)t * M * Du,
+                                  t < H - 1 ? w.Xs : nullptr, st))
+        return err;
+    }
     if (t == H - 1) break;
     if (batched) {
       if (int err = gp_posterior_batched(tab, E, D, nmax, w.Xs, M, w.mean, w.var, w.jmean, w.jvar, bKs, st)) return err;
@@ -953,7 +987,12 @@ extern "C" __attribute__((visibility("default"))) int mcpilco_rollout_fwd(const 
           return err;
       }
     }
-    if (M <= 4096)
+    if (fused_tail)
+      integrate_policy_block_kernel<<<M, policy_block_threads(r->policy.nb), 0, st>>>(
+          r->model, r->meas, r->noise, r->policy, M, t, x_t, w.mean, w.var, w.jmean, w.jvar, r->states + (size_t)(t + 1) * M * Ds,
+          r->need_grad ? r->jac + (size_t)t * M * E * D : nullptr, p_t, meas ? r->pol_in + (size_t)(t + 1) * M * Ds : nullptr, w.nv,
+          r->inputs + (size_t)(t + 1) * M * Du, t + 1 < H - 1 ? w.Xs : nullptr);
+    else if (M <= 4096)
       integrate_warp_kernel<<<cdiv(M, 8), 256, 0, st>>>(r->model, r->meas, r->noise, M, t, x_t, w.mean, w.var, w.jmean, w.jvar,
                                                         r->states + (size_t)(t + 1) * M * Ds,
                                                         r->need_grad ? r->jac + (size_t)t * M * E * D : nullptr, p_t,
